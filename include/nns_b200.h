@@ -1,0 +1,127 @@
+/*
+ * nns_b200.h -- C ABI of the B200-native brute-force nearest-neighbour engine.
+ *
+ * Drop-in boundary for the brute-force path of sty-hhh/NNS-CUDA.  Every entry point cites the
+ * reference interface it replaces (file:line into the reference tree).  Plain pointers and
+ * sizes only; `void *stream` is a cudaStream_t (NULL = the legacy default stream).  There is
+ * no CPU fallback behind any of these calls: without a usable sm_100 GPU they fail with
+ * NNS_B200_ERR_CUDA (the drop-in symbol prints the error and exits, like the reference).
+ *
+ * Semantics shared by all search calls (the reference's V0, core.cu:31-52):
+ *   for each query i the result is the 0-based index j of the reference point with the
+ *   smallest squared L2 distance sum_t (s[i*k+t] - r[j*k+t])^2 accumulated in FP32 over
+ *   ascending t; exact ties resolve to the LOWEST index; a distance that is NaN never wins;
+ *   if no distance is < +INF (including n == 0) the result is 0.
+ */
+#ifndef NNS_B200_H
+#define NNS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNS_B200_VERSION 100
+
+/* status codes of the int-returning entry points */
+#define NNS_B200_OK 0
+#define NNS_B200_ERR_INVALID 1     /* bad argument (negative size, k <= 0, NULL pointer ...) */
+#define NNS_B200_ERR_CUDA 2        /* a CUDA runtime call failed; see nns_b200_last_error()  */
+#define NNS_B200_ERR_UNSUPPORTED 3 /* shape outside what the kernels cover                    */
+#define NNS_B200_ERR_NOMEM 4       /* host or device allocation failed                        */
+
+/* Reference blocks: the device-side reference set ("index") is a tiled structure-of-arrays,
+ * float[num_blocks][k][NNS_B200_REF_BLOCK], padded with NaN to a whole number of blocks.
+ * It replaces the reference's SoA transpose `rr_d` (core.cu:293-306, 362, 367-370). */
+#define NNS_B200_REF_BLOCK 128
+
+/* Packed (distance, index) key: (float_bits(dist) << 32) | (uint32)index.  Distances are
+ * >= +0 so the unsigned (and the signed 64-bit) order of keys is (dist, index) lexicographic:
+ * a plain integer MIN implements "smaller distance, then lower index" exactly.  Replaces the
+ * reference's per-block partial index lists + host re-reduction (core.cu:669-696, 821-852). */
+#define NNS_B200_KEY_INIT 0x7F80000000000000ull /* (+INF, index 0) */
+
+/* flags for nns_b200_search_keys / nns_b200_search_device */
+#define NNS_B200_FLAG_V0_ROUNDING 1u /* round mul and add separately (bit-exact V0 distances;
+                                        1.5x the FP32 work) instead of contracting to FMA   */
+#define NNS_B200_FLAG_FORCE_LOWK 2u  /* testing: force the register-blocked low-k kernel    */
+#define NNS_B200_FLAG_FORCE_WIDE 4u  /* testing: force the reference-parallel generic kernel */
+#define NNS_B200_FLAG_FORCE_TENSOR 8u /* testing: force the tcgen05 path (k multiple of 16) */
+
+/* ---- the drop-in symbol ------------------------------------------------------------------
+ * Replaces vN::cudaCall (core.cu:23-29; same signature in all 14 namespaces) as consumed by
+ * the function pointer `func` (main.cu:7) and called at main.cu:74.  Host pointers in,
+ * row-major s_points[m][k] / r_points[n][k] (core.cu:41, main.cu:27-34), never written.
+ * *results is malloc'd here (core.cu:31) and owned by the caller (free()).  No return code:
+ * on a CUDA failure it prints "Error: file:line, code:N, reason: ..." and exit(1)s exactly
+ * like the reference's CHECK macro (utils.h:16-26).  Synchronous; thread-safe; restores the
+ * caller's current device. */
+void nns_b200_cudaCall(int k, int m, int n, float *s_points, float *r_points, int **results);
+
+/* Same work as nns_b200_cudaCall with a status code and a caller-provided int[m] result. */
+int nns_b200_search_host(int k, int m, int n, const float *s_points, const float *r_points,
+                         int *results);
+
+/* Single-process multi-GPU search over host arrays: replaces v8/v9::cudaCall's OpenMP
+ * fan-out + host merge (core.cu:761-853, 965-1057).  shard_mode 0 = query-sharded (each GPU
+ * gets a query slice and all references), 1 = reference-sharded (contiguous reference
+ * slices, core.cu:781-791; partial results merged by an integer MIN over packed keys, so
+ * results are identical for every num_gpus).  num_gpus <= 0 means all visible devices. */
+int nns_b200_search_multi(int k, int m, int n, const float *s_points, const float *r_points,
+                          int *results, int num_gpus, int shard_mode);
+
+/* ---- lifetime ----------------------------------------------------------------------------
+ * Replaces the load-time WarmUP static initialiser (core.cu:1900-1933): nothing touches the
+ * GPU at load; nns_b200_init(device) creates the per-device state eagerly (device < 0 = the
+ * current device), otherwise it is created lazily by the first call.  nns_b200_shutdown()
+ * releases every cached device/pinned buffer. */
+int nns_b200_init(int device);
+int nns_b200_shutdown(void);
+int nns_b200_version(void);
+const char *nns_b200_last_error(void); /* thread-local text of the last failure */
+
+/* ---- device-resident building blocks (inputs already in HBM) ------------------------------ */
+
+/* number of floats of the tiled-SoA index for n reference points of k dims */
+size_t nns_b200_index_floats(int k, int n);
+
+/* AoS float[n][k] (device) -> tiled SoA index (device, nns_b200_index_floats(k,n) floats,
+ * 16-byte aligned).  Replaces v4::mat_inv_kernel (core.cu:293-306). */
+int nns_b200_index_build(int k, int n, const float *d_refs_aos, float *d_index, void *stream);
+
+/* keys[i] = NNS_B200_KEY_INIT for i < m */
+int nns_b200_keys_init(uint64_t *d_keys, int m, void *stream);
+
+/* The hot path.  For each query i: keys[i] = min(keys[i], key(best distance, index_base + j))
+ * over the n references held in d_index.  d_queries is AoS float[m][k] on the device.
+ * Calling it for several reference shards (each with its own index_base) accumulates the
+ * global minimum.  Replaces v3/v4/v7/v8/v9::cudaCallKernel (core.cu:215-257, 307-349, 589-633,
+ * 716-760, 872-964) and the second-stage reduce (core.cu:669-696). */
+int nns_b200_search_keys(int k, int m, int n, const float *d_queries, const float *d_index,
+                         int index_base, uint64_t *d_keys, unsigned flags, void *stream);
+
+/* d_idx[i] = low 32 bits of keys[i]; d_dist[i] = the FP32 squared distance (may be NULL). */
+int nns_b200_keys_unpack(const uint64_t *d_keys, int m, int *d_idx, float *d_dist, void *stream);
+
+/* Convenience: index_build + keys_init + search_keys + keys_unpack on device arrays.
+ * d_workspace must hold nns_b200_workspace_bytes(k, m, n) bytes (256-byte aligned). */
+size_t nns_b200_workspace_bytes(int k, int m, int n);
+int nns_b200_search_device(int k, int m, int n, const float *d_queries, const float *d_refs_aos,
+                           int *d_idx, void *d_workspace, size_t workspace_bytes, unsigned flags,
+                           void *stream);
+
+/* ---- host-side planning (pure function, no GPU needed; exported for tests) ----------------
+ * Fills plan[0..7] = { path (0 = low-k, 1 = wide, 2 = tensor), queries per thread,
+ * consumer warps per CTA, pipeline stages, query blocks, reference splits, reference blocks
+ * per split, dynamic shared memory bytes } for a device with num_sms SMs. */
+int nns_b200_plan(int k, int m, int n, unsigned flags, int num_sms, int *plan);
+
+/* number of kernels of this library launched by this process so far (bench.py's gpu_launches) */
+unsigned long long nns_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNS_B200_H */

@@ -1,0 +1,219 @@
+"""nns_b200 -- thin ctypes binding of libnns_b200.so (include/nns_b200.h).
+
+This module is plumbing for tests and bench.py: it mirrors the reference's callback surface
+(``cudaCall(k, m, n, s_points, r_points) -> int[m]``, reference core.cu:23-29 / main.cu:74)
+and exposes the device-resident building blocks on torch tensors (torch is used only for
+device memory and streams).  There is NO CPU fallback: if the CUDA library is missing the
+import fails, and every call fails loudly when no sm_100 GPU is usable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint, c_uint64, c_ulonglong, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnns_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, 1, 2, 3, 4
+REF_BLOCK = 128
+KEY_INIT = 0x7F80000000000000
+FLAG_V0_ROUNDING, FLAG_FORCE_LOWK, FLAG_FORCE_WIDE, FLAG_FORCE_TENSOR = 1, 2, 4, 8
+
+
+def flag_overrides(q: int = 0, warps: int = 0, stages: int = 0) -> int:
+    """Tuning overrides packed into the flags word (bits 8-15 q, 16-23 warps, 24-27 stages)."""
+    return (q & 0xFF) << 8 | (warps & 0xFF) << 16 | (stages & 0xF) << 24
+
+
+def nns_plan_q(k: int):
+    """The two register blockings (queries per thread) compiled for dimension k (csrc/nns_plan.h)."""
+    return (8, 4) if k <= 4 else (4, 2) if k <= 16 else (2, 1)
+
+
+class NnsError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"nns_b200 status {status}: {msg}")
+        self.status = status
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make -C nns-cuda_b200` (or __graft_entry__.build()); "
+        "there is no CPU fallback for the search path"
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+_libc = ctypes.CDLL(None)
+_libc.free.argtypes = [c_void_p]
+_libc.free.restype = None
+
+_fp = POINTER(c_float)
+lib.nns_b200_version.restype = c_int
+lib.nns_b200_last_error.restype = c_char_p
+lib.nns_b200_launch_count.restype = c_ulonglong
+lib.nns_b200_init.argtypes = [c_int]
+lib.nns_b200_shutdown.argtypes = []
+lib.nns_b200_cudaCall.argtypes = [c_int, c_int, c_int, _fp, _fp, POINTER(POINTER(c_int))]
+lib.nns_b200_cudaCall.restype = None
+lib.nns_b200_search_host.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+lib.nns_b200_search_multi.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int]
+lib.nns_b200_index_floats.argtypes = [c_int, c_int]
+lib.nns_b200_index_floats.restype = c_size_t
+lib.nns_b200_index_build.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p]
+lib.nns_b200_keys_init.argtypes = [c_void_p, c_int, c_void_p]
+lib.nns_b200_search_keys.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_uint, c_void_p]
+lib.nns_b200_keys_unpack.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+lib.nns_b200_workspace_bytes.argtypes = [c_int, c_int, c_int]
+lib.nns_b200_workspace_bytes.restype = c_size_t
+lib.nns_b200_search_device.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]
+lib.nns_b200_plan.argtypes = [c_int, c_int, c_int, c_uint, c_int, POINTER(c_int)]
+
+
+def _check(status: int) -> None:
+    if status != OK:
+        raise NnsError(status, (lib.nns_b200_last_error() or b"").decode(errors="replace"))
+
+
+def _host_f32(a, rows: int, k: int) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.size != rows * k:
+        raise ValueError(f"expected {rows}x{k} floats, got {a.size}")
+    return a
+
+
+# ---- the reference's callback surface ---------------------------------------------------------
+def cudaCall(k: int, m: int, n: int, s_points, r_points) -> np.ndarray:
+    """Mirror of vN::cudaCall (core.cu:23-29): returns the malloc'd int[m] as a numpy array
+    (copied, then freed with free() as the reference's caller is expected to)."""
+    s = _host_f32(s_points, m, k)
+    r = _host_f32(r_points, n, k)
+    res = POINTER(c_int)()
+    lib.nns_b200_cudaCall(k, m, n, s.ctypes.data_as(_fp), r.ctypes.data_as(_fp), ctypes.byref(res))
+    out = np.ctypeslib.as_array(res, shape=(max(m, 1),))[:m].copy()
+    _libc.free(ctypes.cast(res, c_void_p))
+    return out.astype(np.int32, copy=False)
+
+
+def search_host(k: int, m: int, n: int, s_points, r_points, out: np.ndarray | None = None) -> np.ndarray:
+    """nns_b200_search_host: status-checked variant; accepts numpy arrays or raw host pointers
+    (ints) for s_points / r_points so pinned torch buffers can be passed without a copy."""
+    sp = s_points if isinstance(s_points, int) else _host_f32(s_points, m, k).ctypes.data
+    rp = r_points if isinstance(r_points, int) else _host_f32(r_points, n, k).ctypes.data
+    if out is None:
+        out = np.empty(m, dtype=np.int32)
+    keep = (s_points, r_points)  # keep temporaries alive across the call
+    _check(lib.nns_b200_search_host(k, m, n, sp, rp, out.ctypes.data))
+    del keep
+    return out
+
+
+def search_multi(k: int, m: int, n: int, s_points, r_points, num_gpus: int = 0, shard_mode: int = 0) -> np.ndarray:
+    s = _host_f32(s_points, m, k)
+    r = _host_f32(r_points, n, k)
+    out = np.empty(m, dtype=np.int32)
+    _check(lib.nns_b200_search_multi(k, m, n, s.ctypes.data, r.ctypes.data, out.ctypes.data, num_gpus, shard_mode))
+    return out
+
+
+def plan(k: int, m: int, n: int, flags: int = 0, num_sms: int = 148) -> dict:
+    p = (c_int * 8)()
+    _check(lib.nns_b200_plan(k, m, n, flags, num_sms, p))
+    names = ("path", "q", "warps", "stages", "query_blocks", "splits", "blocks_per_split", "smem")
+    return dict(zip(names, list(p)))
+
+
+def index_floats(k: int, n: int) -> int:
+    return int(lib.nns_b200_index_floats(k, n))
+
+
+def launch_count() -> int:
+    return int(lib.nns_b200_launch_count())
+
+
+def init(device: int = -1) -> None:
+    _check(lib.nns_b200_init(device))
+
+
+def shutdown() -> None:
+    _check(lib.nns_b200_shutdown())
+
+
+# ---- device-resident API on torch tensors (torch = memory + streams only) ----------------------
+def _stream_ptr(stream=None):
+    import torch
+
+    st = stream if stream is not None else torch.cuda.current_stream()
+    return c_void_p(st.cuda_stream)
+
+
+class DeviceIndex:
+    """Build once, query many: the tiled-SoA reference index resident in HBM
+    (replaces the per-call upload + transpose of core.cu:364-370)."""
+
+    def __init__(self, refs, k: int | None = None, index_base: int = 0, stream=None):
+        import torch
+
+        assert refs.is_cuda and refs.dtype == torch.float32 and refs.is_contiguous()
+        self.n = refs.shape[0]
+        self.k = int(k if k is not None else refs.shape[1])
+        self.index_base = int(index_base)
+        self.device = refs.device
+        nfl = index_floats(self.k, self.n)
+        self.index = torch.empty(max(nfl, 4), dtype=torch.float32, device=refs.device)
+        with torch.cuda.device(self.device):
+            _check(lib.nns_b200_index_build(self.k, self.n, refs.data_ptr(), self.index.data_ptr(), _stream_ptr(stream)))
+
+    def new_keys(self, m: int, stream=None):
+        import torch
+
+        keys = torch.empty(max(m, 1), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(lib.nns_b200_keys_init(keys.data_ptr(), m, _stream_ptr(stream)))
+        return keys
+
+    def search_keys(self, queries, keys, flags: int = 0, stream=None):
+        """keys[i] = min(keys[i], key(best dist, index_base + j)) -- the hot path."""
+        import torch
+
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+        m = queries.shape[0]
+        with torch.cuda.device(self.device):
+            _check(lib.nns_b200_search_keys(self.k, m, self.n, queries.data_ptr(), self.index.data_ptr(),
+                                            self.index_base, keys.data_ptr(), flags, _stream_ptr(stream)))
+        return keys
+
+    def search(self, queries, flags: int = 0, stream=None, return_dist: bool = False):
+        import torch
+
+        m = queries.shape[0]
+        keys = self.new_keys(m, stream)
+        self.search_keys(queries, keys, flags, stream)
+        return unpack_keys(keys, m, stream, return_dist)
+
+
+def unpack_keys(keys, m: int, stream=None, return_dist: bool = False):
+    import torch
+
+    idx = torch.empty(max(m, 1), dtype=torch.int32, device=keys.device)
+    dist = torch.empty(max(m, 1), dtype=torch.float32, device=keys.device) if return_dist else None
+    with torch.cuda.device(keys.device):
+        _check(lib.nns_b200_keys_unpack(keys.data_ptr(), m, idx.data_ptr(),
+                                        dist.data_ptr() if dist is not None else None, _stream_ptr(stream)))
+    return (idx[:m], dist[:m]) if return_dist else idx[:m]
+
+
+def search_device(queries, refs, flags: int = 0, stream=None):
+    """One-shot device search: index_build + search + unpack (nns_b200_search_device)."""
+    import torch
+
+    m, k = queries.shape
+    n = refs.shape[0]
+    ws = torch.empty(int(lib.nns_b200_workspace_bytes(k, m, n)), dtype=torch.uint8, device=queries.device)
+    idx = torch.empty(max(m, 1), dtype=torch.int32, device=queries.device)
+    with torch.cuda.device(queries.device):
+        _check(lib.nns_b200_search_device(k, m, n, queries.data_ptr(), refs.data_ptr(), idx.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), flags, _stream_ptr(stream)))
+    return idx[:m]

@@ -1,0 +1,110 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads, exports every symbol include/nns_b200.h
+declares, validates arguments, plans launches sanely, and FAILS LOUDLY (no CPU fallback) when no
+GPU is usable."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nns_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nns_b200_[a-z_A-Z0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_drop_in_symbol_with_reference_signature():
+    text = open(HEADER).read()
+    assert re.search(r"void\s+nns_b200_cudaCall\(int k, int m, int n, float \*s_points, float \*r_points,\s*int \*\*results\);", text)
+    assert "core.cu:23-29" in text and "main.cu:74" in text and "utils.h:16-26" in text
+
+
+def test_library_exports_every_declared_symbol(nns):
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(nns.lib, s), f"{s} declared in include/nns_b200.h but not exported"
+    assert nns.lib.nns_b200_version() == 100
+
+
+def test_header_constants_match_binding(nns):
+    text = open(HEADER).read()
+    assert int(re.search(r"#define NNS_B200_REF_BLOCK (\d+)", text).group(1)) == nns.REF_BLOCK
+    assert int(re.search(r"#define NNS_B200_KEY_INIT (0x[0-9A-Fa-f]+)", text).group(1), 16) == nns.KEY_INIT
+    # (+INF, 0): the float bits of +INF in the high word
+    assert nns.KEY_INIT >> 32 == np.array([np.inf], np.float32).view(np.uint32)[0]
+
+
+def test_index_geometry(nns):
+    assert nns.index_floats(3, 0) == 0
+    assert nns.index_floats(3, 1) == 3 * 128
+    assert nns.index_floats(3, 128) == 3 * 128
+    assert nns.index_floats(3, 129) == 2 * 3 * 128
+    assert nns.index_floats(16, 16777216) == 16 * 16777216
+    assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= 2 * 3 * 128 * 4 + 80
+
+
+def test_argument_validation_needs_no_gpu(nns):
+    out = np.zeros(4, np.int32)
+    s = np.zeros((4, 3), np.float32)
+    assert nns.lib.nns_b200_search_host(0, 4, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_search_host(3, -1, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_search_host(3, 4, 4, None, s.ctypes.data, out.ctypes.data) == nns.ERR_INVALID
+    assert b"NULL" in nns.lib.nns_b200_last_error()
+    assert nns.lib.nns_b200_search_host(3, 0, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data) == nns.OK  # nothing to do
+    assert nns.lib.nns_b200_search_multi(3, 4, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data, 1, 7) == nns.ERR_INVALID
+    with pytest.raises(nns.NnsError):
+        nns.plan(0, 1, 1)
+
+
+def test_no_cpu_fallback_fails_loudly_without_gpu(nns):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the failure path is exercised on the CPU container")
+    s = np.zeros((4, 3), np.float32)
+    with pytest.raises(nns.NnsError) as e:
+        nns.search_host(3, 4, 4, s, s)
+    assert e.value.status == nns.ERR_CUDA
+    assert nns.launch_count() == 0
+
+
+def test_plan_paths(nns):
+    p = nns.plan(3, 65536, 4194304)  # BASELINE config C2
+    assert p["path"] == 0 and p["q"] in (4, 8) and p["warps"] == 8
+    assert p["splits"] * p["blocks_per_split"] >= 4194304 // 128
+    assert (p["splits"] - 1) * p["blocks_per_split"] < 4194304 // 128  # no empty split
+    assert p["blocks_per_split"] % 8 == 0  # whole tiles (k=3: 8 blocks per tile)
+    assert p["smem"] <= 227 * 1024
+    assert nns.plan(128, 1024, 65536)["path"] == 1  # k > 32 -> generic kernel (until the tensor path)
+    assert nns.plan(3, 1, 65536)["path"] == 1  # the reference's m = 1 shapes are reference-parallel
+    assert nns.plan(3, 1, 65536, nns.FLAG_FORCE_LOWK)["path"] == 0
+    assert nns.plan(3, 4096, 65536, nns.FLAG_FORCE_WIDE)["path"] == 1
+    with pytest.raises(nns.NnsError):
+        nns.plan(33, 1024, 1024, nns.FLAG_FORCE_LOWK)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 8, 16, 17, 32])
+@pytest.mark.parametrize("m,n", [(16, 1), (1000, 127), (1024, 65536), (65536, 4194304), (300000, 1000), (16777216, 16777216)])
+def test_plan_covers_every_reference_block_and_query(nns, k, m, n):
+    for q_over in (0,):
+        p = nns.plan(k, m, n, nns.flag_overrides(q=q_over))
+        nblocks = (n + 127) // 128
+        assert p["path"] == 0
+        assert p["query_blocks"] * 32 * p["warps"] * p["q"] >= m
+        assert (p["query_blocks"] - 1) * 32 * p["warps"] * p["q"] < m
+        assert p["splits"] * p["blocks_per_split"] >= nblocks
+        assert (p["splits"] - 1) * p["blocks_per_split"] < max(nblocks, 1)
+        assert 1 <= p["splits"] <= 65535 and p["query_blocks"] >= 1
+
+
+def test_plan_overrides(nns):
+    p = nns.plan(3, 65536, 4194304, nns.flag_overrides(q=4, warps=4, stages=3))
+    assert (p["q"], p["warps"], p["stages"]) == (4, 4, 3)
+    with pytest.raises(nns.NnsError):
+        nns.plan(3, 65536, 4194304, nns.flag_overrides(q=5))
