@@ -42,12 +42,13 @@ struct LowkArgs {
     cudaStream_t stream;
 };
 
-// 4 references (one LDS.128 per dimension) x Q queries.
+// Distances of 4 references (one broadcast LDS.128 per dimension) x Q queries, two references per
+// packed instruction: a01[i] = (d(q_i, r_j0), d(q_i, r_j0+1)), a23[i] = (.., r_j0+2), (.., r_j0+3).
+// Ascending-t accumulation from the first product, like V0 (core.cu:38-43).
 template <int K, int Q, bool EXACT>
-__device__ __forceinline__ void lowk_quad(const float* __restrict__ g, const u64 (&qq)[Q][K],
-                                          unsigned (&best)[Q], int (&bidx)[Q], const int j0)
+__device__ __forceinline__ void lowk_quad_dist(const float* __restrict__ g, const u64 (&qq)[Q][K],
+                                               u64 (&a01)[Q], u64 (&a23)[Q])
 {
-    u64 a01[Q], a23[Q];
 #pragma unroll
     for (int t = 0; t < K; ++t) {
         const ulonglong2 rv = lds_v2u64(g + t * LB);
@@ -67,9 +68,17 @@ __device__ __forceinline__ void lowk_quad(const float* __restrict__ g, const u64
             }
         }
     }
-    // Distances are >= +0 (or NaN = 0x7fffffff, or +INF), so their IEEE bit patterns order like
-    // unsigned integers and NaN sorts last: the argmin bookkeeping runs entirely on the integer
-    // pipe (VIMNMX3 / ISETP), which co-issues with the packed FP32 pipe; FMNMX would not.
+}
+
+// Two-phase argmin over one quad.  Distances are >= +0 (or NaN = 0x7fffffff, or +INF), so their
+// IEEE bit patterns order like unsigned integers and NaN sorts last: the bookkeeping runs entirely
+// on the integer pipe (VIMNMX / VIMNMX3 / ISETP), which co-issues with the packed FP32 pipe.
+// Fast path: min of the four patterns vs the running best.  Rare slow path: ascending rescan with
+// a strict '<' so the first (lowest-index) minimum is kept exactly as V0 does (core.cu:44).
+template <int Q>
+__device__ __forceinline__ void lowk_quad_argmin(const u64 (&a01)[Q], const u64 (&a23)[Q], unsigned (&best)[Q],
+                                                 int (&bidx)[Q], const int j0)
+{
     unsigned mq[Q];
     bool any = false;
 #pragma unroll
@@ -96,8 +105,10 @@ __device__ __forceinline__ void lowk_quad(const float* __restrict__ g, const u64
     }
 }
 
-template <int K, int Q, bool EXACT>
-__global__ void __launch_bounds__(288)
+// MINB = resident CTAs per SM the register allocation is held to, UNROLL = quads per loop body,
+// PIPE = software-pipeline the argmin of quad g-1 under the distances of quad g (see below).
+template <int K, int Q, bool EXACT, int MINB, int UNROLL, bool PIPE>
+__global__ void __launch_bounds__(288, MINB)
 lowk_search_kernel(const float* __restrict__ queries, const int m, const float* __restrict__ index,
                    const int nblocks, const int blocks_per_split, const int index_base,
                    const int stages, u64* __restrict__ keys)
@@ -164,6 +175,15 @@ lowk_search_kernel(const float* __restrict__ queries, const int m, const float* 
         }
     }
 
+    // Software pipeline (PIPE): the argmin bookkeeping of quad g-1 (integer pipe) is issued in the
+    // same basic block as the distance evaluation of quad g (FP32 pipe), so the two pipes overlap
+    // inside every warp instead of alternating.  `pa*` carry the pending quad; they start as
+    // (+INF, +INF), which can never beat a running best.
+    u64 pa01[Q], pa23[Q];
+    int pj = 0;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) { pa01[i] = 0x7f8000007f800000ull; pa23[i] = 0x7f8000007f800000ull; }
+
     int s = 0, round = 0;
     for (int tile = 0; tile < ntiles; ++tile) {
         mbar_wait(full0 + 8u * s, (uint32_t)(round & 1));
@@ -172,9 +192,18 @@ lowk_search_kernel(const float* __restrict__ queries, const int m, const float* 
         int j0 = index_base + (b0 + tile * TB) * LB;
         for (int b = 0; b < tb; ++b) {
             const float* blk = tsm + b * BLOCK_FLOATS;
-#pragma unroll(K <= 8 ? 2 : 1)
+#pragma unroll UNROLL
             for (int g = 0; g < LB / 4; ++g) {
-                lowk_quad<K, Q, EXACT>(blk + 4 * g, qq, best, bidx, j0 + 4 * g);
+                u64 a01[Q], a23[Q];
+                lowk_quad_dist<K, Q, EXACT>(blk + 4 * g, qq, a01, a23);
+                if (PIPE) {
+                    lowk_quad_argmin<Q>(pa01, pa23, best, bidx, pj);
+#pragma unroll
+                    for (int i = 0; i < Q; ++i) { pa01[i] = a01[i]; pa23[i] = a23[i]; }
+                    pj = j0 + 4 * g;
+                } else {
+                    lowk_quad_argmin<Q>(a01, a23, best, bidx, j0 + 4 * g);
+                }
             }
             j0 += LB;
         }
@@ -182,6 +211,7 @@ lowk_search_kernel(const float* __restrict__ queries, const int m, const float* 
         if (lane == 0) mbar_arrive(empty0 + 8u * s);
         if (++s == stages) { s = 0; ++round; }
     }
+    if (PIPE) lowk_quad_argmin<Q>(pa01, pa23, best, bidx, pj);
 
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
@@ -190,10 +220,10 @@ lowk_search_kernel(const float* __restrict__ queries, const int m, const float* 
     }
 }
 
-template <int K, int Q, bool EXACT>
+template <int K, int Q, bool EXACT, int MINB = lowk_minb(K, Q), int UNROLL = lowk_unroll(K), bool PIPE = lowk_pipe(K)>
 cudaError_t lowk_launch_t(const LowkArgs& a, int* occupancy_out)
 {
-    auto kern = lowk_search_kernel<K, Q, EXACT>;
+    auto kern = lowk_search_kernel<K, Q, EXACT, MINB, UNROLL, PIPE>;
     const size_t smem = (size_t)LOWK_BAR_BYTES + (size_t)a.stages * lowk_tile_bytes(K);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

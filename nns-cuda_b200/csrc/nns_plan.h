@@ -21,4 +21,10 @@ NNS_HD constexpr int lowk_tile_bytes(int k) { return lowk_tb(k) * k * 128 * 4; }
 NNS_HD constexpr int lowk_q_default(int k) { return k <= 4 ? 8 : k <= 16 ? 4 : 2; }
 NNS_HD constexpr int lowk_q_alt(int k) { return k <= 4 ? 4 : k <= 16 ? 2 : 1; }
 
+// code-generation choices per (k, q): CTAs/SM the register budget is held to, quads per loop
+// body, software-pipelined argmin (tools/lowk_tune.cu measures the alternatives on a B200)
+NNS_HD constexpr int lowk_minb(int k, int q) { return (k * q <= 16) ? 2 : 1; }
+NNS_HD constexpr int lowk_unroll(int k) { return k <= 8 ? 2 : 1; }
+NNS_HD constexpr bool lowk_pipe(int k) { return true; }
+
 }  // namespace nns
