@@ -307,22 +307,58 @@ def main():
     fp32_peak_tflops = 2.0 * FP32_LANES_PER_SM * SM_COUNT * sm_max_mhz * 1e6 / 1e12
     my_pairs = float(m) * float(r1 - r0)
     kern_pairs_per_s = my_pairs / (kern_ms_avg * 1e-3)
-    if k <= 32:
-        # 2k FP32 lane-slots per pair (k FADD + k FFMA) = 4k FMA-equivalent FLOPs
-        achieved = kern_pairs_per_s * 4.0 * k / 1e12
+    lane_peak = fp32_peak_tflops * 1e12 / 2.0  # FP32 lane-slots per second
+    if k <= 32 and m >= 16 and not (args.flags & nns_b200.FLAG_FORCE_WIDE):
+        # Executed FP32 lane-slots per pair: the screened kernel evaluates
+        # s = |r|^2 - 2q.r with k FMAs per pair; the exact-form kernel runs V0's k subtractions +
+        # k FMAs (2k; 3k with separately rounded mul/add).  `frac` is computed from the slots the
+        # kernel actually executes; `v0_form_frac` prices every pair at V0's 2k slots (the
+        # formulation SURVEY.md 8(d) and the north-star's 70 % bar refer to) and can exceed 1.
+        if args.flags & nns_b200.FLAG_V0_ROUNDING:
+            slots, form = 3 * k, "exact form, V0 rounding"
+        elif args.flags & nns_b200.FLAG_EXACT_FORM:
+            slots, form = 2 * k, "exact form (FADD2 + FFMA2 per dimension)"
+        else:
+            slots, form = k, "norm-expansion screen (FFMA2 per dimension) + exact evaluation of survivors"
+        achieved = kern_pairs_per_s * slots * 2.0 / 1e12
         roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak_tflops, "traffic": None,
+                    "kernel": form, "executed_lane_slots_per_pair": slots,
+                    "v0_form_frac": kern_pairs_per_s * 2.0 * k / lane_peak,
                     "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz ({pk_src} sm_max_mhz; FP32 peak is not in MEASURED_PEAKS.json)",
-                    "work_per_pair": f"{2 * k} FP32 lane-slots = {4 * k} FMA-equivalent FLOPs (strict {3 * k} FLOPs)",
-                    "strict_flop_frac": kern_pairs_per_s * 3.0 * k / 1e12 / fp32_peak_tflops,
                     "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s}
         if clocks.get("sm_mhz"):
-            roofline["frac_at_sampled_clock"] = achieved / (fp32_peak_tflops * clocks["sm_mhz"] / sm_max_mhz)
-    else:
-        achieved = kern_pairs_per_s * 2.0 * k / 1e12
-        peak = float(pk.get("bf16_tflops", 1590.0))
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": f"{pk_src} bf16_tflops (burst)", "kernel_ms": kern_ms_avg}
+            roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
+        if not (args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING)):
+            # the same workload on the exact-form kernel (outside the headline timing), so that
+            # both formulations' FP32-pipe fractions are measured in one run
+            xe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+            for i in range(4):
+                nns_b200._check(nns_b200.lib.nns_b200_keys_init(keys.data_ptr(), m, stream.cuda_stream))
+                if i > 0:
+                    xe[i - 1][0].record(stream)
+                index.search_keys(d_q, keys, args.flags | nns_b200.FLAG_EXACT_FORM, stream)
+                if i > 0:
+                    xe[i - 1][1].record(stream)
+            torch.cuda.synchronize()
+            x_ms = sum(a.elapsed_time(b) for a, b in xe) / len(xe)
+            x_rate = my_pairs / (x_ms * 1e-3)
+            roofline["exact_form_kernel"] = {"kernel_ms": x_ms, "kernel_pairs_per_s": x_rate, "executed_lane_slots_per_pair": 2 * k,
+                                             "frac": x_rate * 2.0 * k / lane_peak}
+    elif k <= 32 or True:
+        # reference-parallel kernel (k > 32 until the tensor path exists, or very few queries)
+        hbm = float(pk.get("hbm_gbs", 6650.0))
+        if m < 16:
+            bytes_per_launch = 4.0 * (k + 1) * (r1 - r0) + 4.0 * k * m + 8.0 * m
+            achieved = bytes_per_launch / (kern_ms_avg * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                        "traffic": None, "peak_source": f"{pk_src} hbm_gbs", "kernel_ms": kern_ms_avg}
+        else:
+            achieved = kern_pairs_per_s * 4.0 * k / 1e12
+            roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                        "frac": achieved / fp32_peak_tflops, "traffic": None, "kernel": "wide (reference-parallel) kernel",
+                        "executed_lane_slots_per_pair": 2 * k, "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s,
+                        "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz"}
 
     line = {
         "metric": "pair_dist_evals_per_s", "value": value, "unit": "pairs/s", "queries_per_s": queries_per_s,

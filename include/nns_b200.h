@@ -32,9 +32,11 @@ extern "C" {
 #define NNS_B200_ERR_UNSUPPORTED 3 /* shape outside what the kernels cover                    */
 #define NNS_B200_ERR_NOMEM 4       /* host or device allocation failed                        */
 
-/* Reference blocks: the device-side reference set ("index") is a tiled structure-of-arrays,
- * float[num_blocks][k][NNS_B200_REF_BLOCK], padded with NaN to a whole number of blocks.
- * It replaces the reference's SoA transpose `rr_d` (core.cu:293-306, 362, 367-370). */
+/* Reference blocks: the device-side reference set ("index") is a tiled structure-of-arrays:
+ * a 32-float header (header[0] = max |r|^2), then float[num_blocks][k + 1][NNS_B200_REF_BLOCK]
+ * -- k coordinate rows and one |r|^2 row per block of 128 points -- padded with NaN to a whole
+ * number of blocks.  It replaces the reference's SoA transpose `rr_d` (core.cu:293-306, 362,
+ * 367-370). */
 #define NNS_B200_REF_BLOCK 128
 
 /* Packed (distance, index) key: (float_bits(dist) << 32) | (uint32)index.  Distances are
@@ -49,6 +51,11 @@ extern "C" {
 #define NNS_B200_FLAG_FORCE_LOWK 2u  /* testing: force the register-blocked low-k kernel    */
 #define NNS_B200_FLAG_FORCE_WIDE 4u  /* testing: force the reference-parallel generic kernel */
 #define NNS_B200_FLAG_FORCE_TENSOR 8u /* testing: force the tcgen05 path (k multiple of 16) */
+#define NNS_B200_FLAG_EXACT_FORM 16u /* evaluate every pair in V0's subtract-square form (2k FP32
+                                        lane-slots per pair) instead of screening pairs with the
+                                        norm expansion and evaluating only the survivors that way;
+                                        both return the same indices                          */
+/* bits 8-15 / 16-23 / 24-27: tuning overrides (queries per thread, warps per CTA, ring stages) */
 
 /* ---- the drop-in symbol ------------------------------------------------------------------
  * Replaces vN::cudaCall (core.cu:23-29; same signature in all 14 namespaces) as consumed by

@@ -74,7 +74,7 @@ struct Plan {
     int smem;    // dynamic shared memory bytes
 };
 
-typedef int (*occ_fn)(void* user, int k, int q, bool exact, int warps, int stages);
+typedef int (*occ_fn)(void* user, int k, int q, int mode, int warps, int stages);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -83,7 +83,7 @@ static int est_ctas_per_sm(int k, int q, int warps, int stages)
 {
     const int threads = (warps + 1) * 32;
     const int smem = LOWK_BAR_BYTES + stages * lowk_tile_bytes(k);
-    int regs = 38 + q * (k + 9);
+    int regs = 40 + q * (k + 10);
     if (regs > 224) regs = 224;
     regs = (regs + 7) & ~7;
     int by_regs = 65536 / (regs * threads);
@@ -119,11 +119,19 @@ static void choose_splits(int nqb, int nblocks, int tb, int slots, double overhe
     if (cost) *cost = best;
 }
 
+static int lowk_mode_of(unsigned flags)
+{
+    if (flags & NNS_B200_FLAG_V0_ROUNDING) return LOWK_EXACT_V0;
+    if (flags & NNS_B200_FLAG_EXACT_FORM) return LOWK_EXACT_FMA;
+    return LOWK_FILTER;
+}
+
 static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn occ, void* occ_user, Plan* p)
 {
     if (k <= 0 || m < 0 || n < 0) return fail(NNS_B200_ERR_INVALID, "invalid shape k=%d m=%d n=%d", k, m, n);
     if (num_sms <= 0) num_sms = 148;
-    const bool exact = (flags & NNS_B200_FLAG_V0_ROUNDING) != 0;
+    const int mode = lowk_mode_of(flags);
+    const bool exact = mode == LOWK_EXACT_V0;
     const int nblocks = ceil_div(n, LB);
     memset(p, 0, sizeof(*p));
     if (flags & NNS_B200_FLAG_FORCE_TENSOR)
@@ -164,19 +172,20 @@ static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn oc
     const int qs[2] = {lowk_q_default(k), lowk_q_alt(k)};
     for (int qi = 0; qi < 2; ++qi) {
         const int q = qs[qi];
-        if (q_over && q != q_over) continue;
+        if (q_over ? q != q_over : qi != 0) continue;  // the alternative blocking only on request
         if (exact && q != lowk_q_default(k)) continue;
         for (int w = 8; w >= 1; w >>= 1) {
             if (w_over && w != w_over) continue;
             const int qb = 32 * w * q;
             const int nqb = ceil_div(m, qb);
-            int cps = occ ? occ(occ_user, k, q, exact, w, stages) : est_ctas_per_sm(k, q, w, stages);
+            int cps = occ ? occ(occ_user, k, q, mode, w, stages) : est_ctas_per_sm(k, q, w, stages);
             if (cps < 1) cps = 1;
             const int slots = num_sms * cps;
             // work of one CTA per reference block, in SM cycles: 128 refs * q queries * 2k FP32
             // lane-slots per lane; W*cps warps share 4 schedulers
             const double share = (double)(w * cps) / 4.0;
-            const double block_cycles = 128.0 * q * 2.0 * k * (share > 1.0 ? share : 1.0) * (1.0 + 0.15 / q);
+            const double lane_slots = (mode == LOWK_FILTER ? 1.0 : mode == LOWK_EXACT_FMA ? 2.0 : 3.0) * k + 1.5;
+            const double block_cycles = 128.0 * q * lane_slots * (share > 1.0 ? share : 1.0) * (1.0 + 0.15 / q);
             const double overhead_blocks = 6000.0 / block_cycles;  // launch/prologue/atomics
             int s, bps;
             double c;
@@ -197,19 +206,16 @@ static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn oc
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
-static cudaError_t lowk_dispatch(int k, int q, bool exact, const LowkArgs& a, int* occ)
+static cudaError_t lowk_dispatch(int k, int q, int mode, const LowkArgs& a, int* occ)
 {
-    switch ((k - 1) / 4) {
-        case 0: return lowk_launch_range_0(k, q, exact, a, occ);
-        case 1: return lowk_launch_range_1(k, q, exact, a, occ);
-        case 2: return lowk_launch_range_2(k, q, exact, a, occ);
-        case 3: return lowk_launch_range_3(k, q, exact, a, occ);
-        case 4: return lowk_launch_range_4(k, q, exact, a, occ);
-        case 5: return lowk_launch_range_5(k, q, exact, a, occ);
-        case 6: return lowk_launch_range_6(k, q, exact, a, occ);
-        case 7: return lowk_launch_range_7(k, q, exact, a, occ);
-        default: return cudaErrorInvalidValue;
-    }
+    typedef cudaError_t (*range_fn)(int, int, int, const LowkArgs&, int*);
+    static const range_fn table[16] = {
+        lowk_launch_range_0,  lowk_launch_range_1,  lowk_launch_range_2,  lowk_launch_range_3,
+        lowk_launch_range_4,  lowk_launch_range_5,  lowk_launch_range_6,  lowk_launch_range_7,
+        lowk_launch_range_8,  lowk_launch_range_9,  lowk_launch_range_10, lowk_launch_range_11,
+        lowk_launch_range_12, lowk_launch_range_13, lowk_launch_range_14, lowk_launch_range_15};
+    if (k < 1 || k > LOWK_MAX_K) return cudaErrorInvalidValue;
+    return table[(k - 1) / 2](k, q, mode, a, occ);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -280,17 +286,17 @@ static int buf_reserve(DevBuf* b, size_t bytes)
     return NNS_B200_OK;
 }
 
-static int occ_query(void* user, int k, int q, bool exact, int warps, int stages)
+static int occ_query(void* user, int k, int q, int mode, int warps, int stages)
 {
     DeviceCtx* c = (DeviceCtx*)user;
-    const auto key = std::make_tuple(k, q, (int)exact, warps, stages);
+    const auto key = std::make_tuple(k, q, mode, warps, stages);
     auto it = c->occ_cache.find(key);
     if (it != c->occ_cache.end()) return it->second;
     LowkArgs a{};
     a.warps = warps;
     a.stages = stages;
     int occ = 0;
-    if (lowk_dispatch(k, q, exact, a, &occ) != cudaSuccess) {
+    if (lowk_dispatch(k, q, mode, a, &occ) != cudaSuccess) {
         cudaGetLastError();
         occ = 0;
     }
@@ -300,26 +306,26 @@ static int occ_query(void* user, int k, int q, bool exact, int warps, int stages
 
 // The hot path on device-resident data: plan, launch.  `c` supplies num_sms and the occupancy
 // cache; the caller must have made c->device current.
-static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, const float* d_index,
-                          int index_base, u64* d_keys, unsigned flags, cudaStream_t st)
+static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, const float* d_header,
+                          const float* d_blocks, int index_base, u64* d_keys, unsigned flags, cudaStream_t st)
 {
     if (m == 0 || n == 0) return NNS_B200_OK;
     Plan p;
     ST_TRY(make_plan(k, m, n, flags, c->num_sms, occ_query, c, &p));
-    const bool exact = (flags & NNS_B200_FLAG_V0_ROUNDING) != 0;
+    const int mode = lowk_mode_of(flags);
     const int nblocks = ceil_div(n, LB);
     if (p.path == 0) {
         LowkArgs a{};
-        a.queries = d_queries; a.m = m; a.index = d_index; a.nblocks = nblocks;
+        a.queries = d_queries; a.m = m; a.header = d_header; a.blocks = d_blocks; a.nblocks = nblocks;
         a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
         a.warps = p.warps; a.stages = p.stages; a.nqb = p.nqb; a.splits = p.splits; a.stream = st;
-        CU_TRY(lowk_dispatch(k, p.q, exact, a, nullptr));
+        CU_TRY(lowk_dispatch(k, p.q, mode, a, nullptr));
     } else {
         WideArgs a{};
-        a.queries = d_queries; a.m = m; a.k = k; a.index = d_index; a.nblocks = nblocks;
+        a.queries = d_queries; a.m = m; a.k = k; a.blocks = d_blocks; a.nblocks = nblocks;
         a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
         a.nqg = p.nqb; a.splits = p.splits; a.stream = st;
-        CU_TRY(wide_launch(exact, a));
+        CU_TRY(wide_launch(mode == LOWK_EXACT_V0, a));
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return NNS_B200_OK;
@@ -340,6 +346,8 @@ struct DeviceGuard {
         if (active && prev >= 0) cudaSetDevice(prev);
     }
 };
+
+static unsigned host_flags();
 
 // Host arrays -> device -> keys (h_keys != NULL) or indices (h_idx != NULL) on the host.
 // References are ingested in chunks: the H2D copy of chunk c+1 (copy stream) overlaps the
@@ -385,10 +393,11 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
                                cudaMemcpyHostToDevice, c->copy));
         CU_TRY(cudaEventRecord(c->events[ci], c->copy));
         CU_TRY(cudaStreamWaitEvent(c->compute, c->events[ci], 0));
-        float* d_index_c = d_index + (j0 / LB) * (long long)k * LB;
-        CU_TRY(launch_index_build(k, cn, d_r + j0 * k, d_index_c, c->compute));
+        float* d_blocks_c = d_index + INDEX_HEADER_FLOATS + (j0 / LB) * (long long)index_block_floats(k);
+        CU_TRY(launch_index_build(k, cn, d_r + j0 * k, d_index, d_blocks_c, ci == 0, c->compute));
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        ST_TRY(search_keys_on(c, k, m, cn, d_q, d_index_c, index_base + (int)j0, d_keys, 0, c->compute));
+        ST_TRY(search_keys_on(c, k, m, cn, d_q, d_index, d_blocks_c, index_base + (int)j0, d_keys, host_flags(),
+                              c->compute));
     }
     if (h_keys) {
         CU_TRY(cudaMemcpyAsync(h_keys, d_keys, (size_t)m * sizeof(u64), cudaMemcpyDeviceToHost, c->compute));
@@ -400,6 +409,17 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
     CU_TRY(cudaStreamSynchronize(c->compute));
     CU_TRY(cudaStreamSynchronize(c->copy));
     return NNS_B200_OK;
+}
+
+// NNS_B200_FLAGS (environment, a C integer literal) applies the flags word to the host-pointer
+// entry points, whose reference signature has no flags argument.
+static unsigned host_flags()
+{
+    static const unsigned f = []() {
+        const char* e = getenv("NNS_B200_FLAGS");
+        return e ? (unsigned)strtoul(e, nullptr, 0) : 0u;
+    }();
+    return f;
 }
 
 static int check_host_args(int k, int m, int n, const void* s, const void* r, const void* out)
@@ -457,7 +477,7 @@ int nns_b200_shutdown(void)
 size_t nns_b200_index_floats(int k, int n)
 {
     if (k <= 0 || n <= 0) return 0;
-    return (size_t)ceil_div(n, LB) * (size_t)k * LB;
+    return (size_t)INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * (size_t)index_block_floats(k);
 }
 
 int nns_b200_index_build(int k, int n, const float* d_refs_aos, float* d_index, void* stream)
@@ -465,7 +485,7 @@ int nns_b200_index_build(int k, int n, const float* d_refs_aos, float* d_index, 
     if (k <= 0 || n < 0) return fail(NNS_B200_ERR_INVALID, "invalid shape k=%d n=%d", k, n);
     if (n > 0 && (!d_refs_aos || !d_index)) return fail(NNS_B200_ERR_INVALID, "NULL array");
     if (((uintptr_t)d_index & 15) != 0) return fail(NNS_B200_ERR_INVALID, "index must be 16-byte aligned");
-    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, (cudaStream_t)stream));
+    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_index + INDEX_HEADER_FLOATS, true, (cudaStream_t)stream));
     g_launches.fetch_add(n > 0 ? 1 : 0, std::memory_order_relaxed);
     return NNS_B200_OK;
 }
@@ -496,7 +516,8 @@ int nns_b200_search_keys(int k, int m, int n, const float* d_queries, const floa
     DeviceCtx* c;
     ST_TRY(ctx_get(-1, &c));
     std::lock_guard<std::mutex> lk(c->mu);
-    return search_keys_on(c, k, m, n, d_queries, d_index, index_base, (u64*)d_keys, flags, (cudaStream_t)stream);
+    return search_keys_on(c, k, m, n, d_queries, d_index, d_index + INDEX_HEADER_FLOATS, index_base, (u64*)d_keys, flags,
+                          (cudaStream_t)stream);
 }
 
 size_t nns_b200_workspace_bytes(int k, int m, int n)
@@ -522,9 +543,9 @@ int nns_b200_search_device(int k, int m, int n, const float* d_queries, const fl
     ST_TRY(ctx_get(-1, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     CU_TRY(launch_keys_init(d_keys, m, st));
-    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, st));
+    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_index + INDEX_HEADER_FLOATS, true, st));
     g_launches.fetch_add(n > 0 ? 3 : 2, std::memory_order_relaxed);  // + the unpack below
-    ST_TRY(search_keys_on(c, k, m, n, d_queries, d_index, 0, d_keys, flags, st));
+    ST_TRY(search_keys_on(c, k, m, n, d_queries, d_index, d_index + INDEX_HEADER_FLOATS, 0, d_keys, flags, st));
     CU_TRY(launch_keys_unpack(d_keys, m, d_idx, nullptr, st));
     return NNS_B200_OK;
 }

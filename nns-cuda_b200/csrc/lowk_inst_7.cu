@@ -1,5 +1,5 @@
-// lowk_inst_7.cu -- instantiates the low-k search kernels for k = 29..32 (split for parallel builds)
-#define LOWK_K_LO 29
-#define LOWK_K_HI 32
+// lowk_inst_7.cu -- instantiates the low-k search kernels for k = 15..16 (split for parallel builds)
+#define LOWK_K_LO 15
+#define LOWK_K_HI 16
 #define LOWK_RANGE_FN lowk_launch_range_7
 #include "lowk_inst.cuh"

@@ -7,7 +7,8 @@
 namespace nns {
 
 // index_build.cu
-cudaError_t launch_index_build(int k, int n, const float* d_refs_aos, float* d_index, cudaStream_t st);
+cudaError_t launch_index_build(int k, int n, const float* d_refs_aos, float* d_header, float* d_blocks,
+                               bool reset_header, cudaStream_t st);
 cudaError_t launch_keys_init(u64* d_keys, int m, cudaStream_t st);
 cudaError_t launch_keys_unpack(const u64* d_keys, int m, int* d_idx, float* d_dist, cudaStream_t st);
 
@@ -15,7 +16,7 @@ cudaError_t launch_keys_unpack(const u64* d_keys, int m, int* d_idx, float* d_di
 struct WideArgs {
     const float* queries;  // device AoS [m][k]
     int m, k;
-    const float* index;    // tiled SoA
+    const float* blocks;   // first reference block of the range: [nblocks][k+1][128]
     int nblocks;
     int blocks_per_split;
     int index_base;
@@ -26,14 +27,22 @@ struct WideArgs {
 };
 cudaError_t wide_launch(bool exact, const WideArgs& a);
 
-// lowk_inst_N.cu
-cudaError_t lowk_launch_range_0(int k, int q, bool exact, const LowkArgs& a, int* occ);
-cudaError_t lowk_launch_range_1(int k, int q, bool exact, const LowkArgs& a, int* occ);
-cudaError_t lowk_launch_range_2(int k, int q, bool exact, const LowkArgs& a, int* occ);
-cudaError_t lowk_launch_range_3(int k, int q, bool exact, const LowkArgs& a, int* occ);
-cudaError_t lowk_launch_range_4(int k, int q, bool exact, const LowkArgs& a, int* occ);
-cudaError_t lowk_launch_range_5(int k, int q, bool exact, const LowkArgs& a, int* occ);
-cudaError_t lowk_launch_range_6(int k, int q, bool exact, const LowkArgs& a, int* occ);
-cudaError_t lowk_launch_range_7(int k, int q, bool exact, const LowkArgs& a, int* occ);
+// lowk_inst_N.cu (N = (k-1)/2)
+cudaError_t lowk_launch_range_0(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_1(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_2(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_3(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_4(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_5(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_6(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_7(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_8(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_9(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_10(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_11(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_12(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_13(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_14(int k, int q, int mode, const LowkArgs& a, int* occ);
+cudaError_t lowk_launch_range_15(int k, int q, int mode, const LowkArgs& a, int* occ);
 
 }  // namespace nns

@@ -13,10 +13,12 @@
 
 namespace nns {
 
+static_assert(WIDE_QT == 4, "the query tile is read as float4");
+
 template <bool EXACT>
 __global__ void __launch_bounds__(WIDE_THREADS)
 wide_search_kernel(const float* __restrict__ queries, const int m, const int k,
-                   const float* __restrict__ index, const int nblocks, const int blocks_per_split,
+                   const float* __restrict__ blocks, const int nblocks, const int blocks_per_split,
                    const int index_base, u64* __restrict__ keys)
 {
     extern __shared__ __align__(16) float qs[];  // [k][WIDE_QT]
@@ -40,7 +42,7 @@ wide_search_kernel(const float* __restrict__ queries, const int m, const int k,
     for (int i = 0; i < WIDE_QT; ++i) { best[i] = inf_f(); bidx[i] = 0; }
 
     for (int b = b0 + half; b < b1; b += WIDE_THREADS / LB) {
-        const float* blk = index + (size_t)b * k * LB + l;
+        const float* blk = blocks + (size_t)b * (k + 1) * LB + l;  // rows 0..k-1 (row k = |r|^2 is not used here)
         float acc[WIDE_QT];
 #pragma unroll
         for (int i = 0; i < WIDE_QT; ++i) acc[i] = 0.0f;
@@ -101,12 +103,12 @@ cudaError_t wide_launch(bool exact, const WideArgs& a)
         e = cudaFuncSetAttribute(wide_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         wide_search_kernel<true><<<grid, WIDE_THREADS, smem, a.stream>>>(
-            a.queries, a.m, a.k, a.index, a.nblocks, a.blocks_per_split, a.index_base, a.keys);
+            a.queries, a.m, a.k, a.blocks, a.nblocks, a.blocks_per_split, a.index_base, a.keys);
     } else {
         e = cudaFuncSetAttribute(wide_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         wide_search_kernel<false><<<grid, WIDE_THREADS, smem, a.stream>>>(
-            a.queries, a.m, a.k, a.index, a.nblocks, a.blocks_per_split, a.index_base, a.keys);
+            a.queries, a.m, a.k, a.blocks, a.nblocks, a.blocks_per_split, a.index_base, a.keys);
     }
     return cudaGetLastError();
 }

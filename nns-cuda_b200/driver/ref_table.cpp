@@ -1,0 +1,63 @@
+// ref_table.cpp -- a stand-alone benchmark driver with the reference's shape table, seed, data
+// generator, timing convention and print format (main.cu:10-13, 24-35, 38-51, 62-80), calling the
+// B200 engine through the same function-pointer type the reference's driver uses (main.cu:7, 74).
+// Its output lines can be diffed against the reference's `./main` (profiles/r1_ref_main_b200.txt).
+// This is SURVEY.md section 8(f) row n1; it is a caller of the hot path, not part of it.
+//
+//   g++ -O2 -I../../include -I../shim ref_table.cpp -L../lib -lnns_b200 -Wl,-rpath,'$ORIGIN/../lib' -o ref_table
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+
+#include "nns_b200.hpp"
+
+static void (*func)(int, int, int, float *, float *, int **);  // main.cu:7
+
+static long get_time_ns()  // utils.h:9-13
+{
+    struct timespec ts;
+    timespec_get(&ts, TIME_UTC);
+    return (long)ts.tv_sec * 1000000000L + ts.tv_nsec;
+}
+
+static float get_rand() { return (float)(rand() / double(RAND_MAX)); }  // main.cu:10-13
+
+static void get_sample(int k, int m, int n, float **s_points, float **r_points)  // main.cu:24-35
+{
+    float *tmp = (float *)malloc(sizeof(float) * (size_t)k * m);
+    for (long i = 0; i < (long)k * m; i++) tmp[i] = get_rand();
+    *s_points = tmp;
+    tmp = (float *)malloc(sizeof(float) * (size_t)k * n);
+    for (long i = 0; i < (long)k * n; i++) tmp[i] = get_rand();
+    *r_points = tmp;
+}
+
+// main.cu:38-51
+static const int samples[] = {3, 1, 1024,    16, 1, 1024,    3, 1, 65536,      16, 1, 65536,      3, 1024, 1024,
+                              16, 1024, 1024, 3, 1024, 65536, 16, 1024, 65536, 3, 1024, 1048576, 16, 1024, 1048576};
+
+int main(int argc, char **argv)
+{
+    const int version = 14;  // the reference's own variants are 0..13 (main.cu:87-135)
+    const int reps = argc > 1 ? atoi(argv[1]) : 1;
+    func = &b200::cudaCall;
+    const int total = (int)(sizeof(samples) / (3 * sizeof(*samples)));
+    printf("\nRunning CUDACALL %d...\n", version);  // main.cu:136
+    for (int rep = 0; rep < reps; ++rep) {
+        srand(1000);  // main.cu:54, 64
+        for (int i = 0; i < total; ++i) {
+            const int k = samples[3 * i], m = samples[3 * i + 1], n = samples[3 * i + 2];
+            float *s_points, *r_points;
+            get_sample(k, m, n, &s_points, &r_points);
+            int *results;
+            const long st = get_time_ns();
+            (*func)(k, m, n, s_points, r_points, &results);
+            const long et = get_time_ns();
+            printf("CudaCall %d, %2d, %4d, %10d, %10.3fms\n", version, k, m, n, (et - st) / 1e6);  // main.cu:76
+            free(results);  // the reference's driver leaks this (main.cu:72-78)
+            free(s_points);
+            free(r_points);
+        }
+    }
+    return 0;
+}

@@ -20,7 +20,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnns_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, 1, 2, 3, 4
 REF_BLOCK = 128
 KEY_INIT = 0x7F80000000000000
-FLAG_V0_ROUNDING, FLAG_FORCE_LOWK, FLAG_FORCE_WIDE, FLAG_FORCE_TENSOR = 1, 2, 4, 8
+FLAG_V0_ROUNDING, FLAG_FORCE_LOWK, FLAG_FORCE_WIDE, FLAG_FORCE_TENSOR, FLAG_EXACT_FORM = 1, 2, 4, 8, 16
+INDEX_HEADER_FLOATS = 32
 
 
 def flag_overrides(q: int = 0, warps: int = 0, stages: int = 0) -> int:
@@ -30,7 +31,7 @@ def flag_overrides(q: int = 0, warps: int = 0, stages: int = 0) -> int:
 
 def nns_plan_q(k: int):
     """The two register blockings (queries per thread) compiled for dimension k (csrc/nns_plan.h)."""
-    return (8, 4) if k <= 4 else (4, 2) if k <= 16 else (2, 1)
+    return (4, 8) if k <= 4 else (4, 2) if k <= 8 else (2, 4) if k <= 16 else (2, 1)
 
 
 class NnsError(RuntimeError):

@@ -41,12 +41,13 @@ def test_header_constants_match_binding(nns):
 
 
 def test_index_geometry(nns):
+    # 32-float header + (k coordinate rows + 1 norm row) x 128 lanes per block of 128 points
     assert nns.index_floats(3, 0) == 0
-    assert nns.index_floats(3, 1) == 3 * 128
-    assert nns.index_floats(3, 128) == 3 * 128
-    assert nns.index_floats(3, 129) == 2 * 3 * 128
-    assert nns.index_floats(16, 16777216) == 16 * 16777216
-    assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= 2 * 3 * 128 * 4 + 80
+    assert nns.index_floats(3, 1) == 32 + 4 * 128
+    assert nns.index_floats(3, 128) == 32 + 4 * 128
+    assert nns.index_floats(3, 129) == 32 + 2 * 4 * 128
+    assert nns.index_floats(16, 16777216) == 32 + 17 * 16777216
+    assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= (32 + 2 * 4 * 128) * 4 + 80
 
 
 def test_argument_validation_needs_no_gpu(nns):
@@ -104,7 +105,7 @@ def test_plan_covers_every_reference_block_and_query(nns, k, m, n):
 
 
 def test_plan_overrides(nns):
-    p = nns.plan(3, 65536, 4194304, nns.flag_overrides(q=4, warps=4, stages=3))
-    assert (p["q"], p["warps"], p["stages"]) == (4, 4, 3)
+    p = nns.plan(3, 65536, 4194304, nns.flag_overrides(q=8, warps=4, stages=3))
+    assert (p["q"], p["warps"], p["stages"]) == (8, 4, 3)
     with pytest.raises(nns.NnsError):
         nns.plan(3, 65536, 4194304, nns.flag_overrides(q=5))

@@ -56,11 +56,13 @@ def test_known_answers_through_the_drop_in_symbol(nns):
 
 
 @pytest.mark.parametrize("path", ["auto", "lowk", "wide"])
-@pytest.mark.parametrize("rounding", ["v0", "fma"])
+@pytest.mark.parametrize("rounding", ["v0", "fma", "filter"])
 def test_golden_vectors(nns, oracle, torch_mod, path, rounding):
     flags = {"auto": 0, "lowk": nns.FLAG_FORCE_LOWK, "wide": nns.FLAG_FORCE_WIDE}[path]
     if rounding == "v0":
         flags |= nns.FLAG_V0_ROUNDING
+    elif rounding == "fma":
+        flags |= nns.FLAG_EXACT_FORM
     ran = 0
     for kind, k, m, n, seed, idx, _ in golden_cases():
         if path == "lowk" and k > 32:
@@ -101,9 +103,13 @@ def test_lowk_shape_sweep_identical_with_v0_rounding(nns, oracle, torch_mod, k, 
     assert np.array_equal(g, v)
     from nns_b200 import nns_plan_q
 
-    for q in nns_plan_q(k):  # both register blockings, FMA mode: north-star rule
-        g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_LOWK | nns.flag_overrides(q=q))
-        assert_rule(oracle, k, m, n, s, r, g, v, False)
+    ref = None
+    for q in nns_plan_q(k):  # both register blockings, FMA modes: north-star rule
+        for form in (nns.FLAG_EXACT_FORM, 0):  # every pair in V0 form / norm-expansion screen + exact survivors
+            g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_LOWK | form | nns.flag_overrides(q=q))
+            assert_rule(oracle, k, m, n, s, r, g, v, False)
+            ref = g if ref is None else ref
+            assert np.array_equal(g, ref)  # the screen never changes the answer
 
 
 @pytest.mark.parametrize("k", [3, 16])
@@ -116,8 +122,9 @@ def test_lowk_every_cta_geometry(nns, oracle, torch_mod, k, warps):
 
     for q in nns_plan_q(k):
         for stages in (2, 4):
-            g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_LOWK | nns.flag_overrides(q=q, warps=warps, stages=stages))
-            assert np.array_equal(g, v), (k, warps, q, stages)  # grid data: exact in FMA mode too
+            for form in (0, nns.FLAG_EXACT_FORM):
+                g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_LOWK | form | nns.flag_overrides(q=q, warps=warps, stages=stages))
+                assert np.array_equal(g, v), (k, warps, q, stages, form)  # grid data: exact in FMA mode too
 
 
 @pytest.mark.parametrize("k,m,n", [(33, 20, 900), (64, 37, 3000), (128, 64, 4096), (200, 5, 1000), (3, 1, 70000), (16, 3, 33000), (3, 7, 129)])
@@ -140,9 +147,50 @@ def test_special_values(nns, oracle, torch_mod):
     r[17] = -np.inf
     v = oracle.v0(k, m, n, s, r)
     assert v[1] == 0 and v[2] == 0 and v[3] == 0
-    for flags in (nns.FLAG_FORCE_LOWK, nns.FLAG_FORCE_WIDE, nns.FLAG_FORCE_LOWK | nns.FLAG_V0_ROUNDING):
+    for flags in (nns.FLAG_FORCE_LOWK, nns.FLAG_FORCE_LOWK | nns.FLAG_EXACT_FORM, nns.FLAG_FORCE_WIDE,
+                  nns.FLAG_FORCE_LOWK | nns.FLAG_V0_ROUNDING):
         g = gpu_search(nns, torch_mod, s, r, flags)
         assert np.array_equal(g, v), flags
+
+
+@pytest.mark.parametrize("k", [3, 16])
+@pytest.mark.parametrize("case", ["offset1000", "offset1e6", "tiny", "huge1e15", "huge1e25", "denormal", "mixed_scale", "nan_refs"])
+def test_filter_adversarial_magnitudes(nns, oracle, torch_mod, k, case):
+    """The norm-expansion screen must never change the answer: data built to stress its error bound
+    (large common offsets => catastrophic cancellation in |r|^2 - 2q.r, magnitudes that overflow
+    FP32 norms, denormals, mixed scales, NaN reference points).  The screened kernel must return
+    exactly what the exact-form kernel returns, which must satisfy the rule against V0."""
+    m, n = 600, 20000
+    s, r = make_case("uniform", k, m, n, 31)
+    s, r = s.astype(np.float64), r.astype(np.float64)
+    if case == "offset1000":
+        s, r = s + 1000.0, r + 1000.0
+    elif case == "offset1e6":
+        s, r = s * 4 + 1e6, r * 4 + 1e6
+    elif case == "tiny":
+        s, r = s * 1e-18, r * 1e-18
+    elif case == "huge1e15":
+        s, r = s * 1e15, r * 1e15
+    elif case == "huge1e25":  # |r|^2 overflows FP32: the screen must disable itself
+        s, r = s * 1e25, r * 1e25
+    elif case == "denormal":
+        s, r = s * 1e-42, r * 1e-42
+    elif case == "mixed_scale":
+        r[::7] *= 1e6
+        s[::5] *= 1e-4
+    s, r = s.astype(np.float32), r.astype(np.float32)
+    if case == "nan_refs":
+        r[::11] = np.nan
+        r[5, 1] = np.inf
+    v = oracle.v0(k, m, n, s, r)
+    ge = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_LOWK | nns.FLAG_EXACT_FORM)
+    gf = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_LOWK)
+    assert np.array_equal(gf, ge), int((gf != ge).sum())
+    gv = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_LOWK | nns.FLAG_V0_ROUNDING)
+    assert np.array_equal(gv, v)
+    if case not in ("huge1e25", "denormal"):  # there FP32 distances overflow / underflow to 0 in V0 itself; V0 equality above covers it
+        rep = oracle.check_tie_rule(k, m, n, s, r, gf, v, REL_TOL)
+        assert rep["outside_band"] == 0 and rep["out_of_range"] == 0, rep
 
 
 def test_duplicates_resolve_to_lowest_index_everywhere(nns, oracle, torch_mod):
@@ -150,7 +198,7 @@ def test_duplicates_resolve_to_lowest_index_everywhere(nns, oracle, torch_mod):
     k, m, n = 3, 8192, 200000
     s, r = make_case("clustered", k, m, n, 1000)
     v, _ = oracle.v0_omp(k, m, n, s, r)
-    for flags in (0, nns.flag_overrides(q=4), nns.FLAG_FORCE_WIDE):
+    for flags in (0, nns.flag_overrides(q=8), nns.FLAG_EXACT_FORM, nns.FLAG_FORCE_WIDE):
         if flags == nns.FLAG_FORCE_WIDE:
             g = gpu_search(nns, torch_mod, s[:512], r, flags)
             assert np.array_equal(g, v[:512])
@@ -218,9 +266,11 @@ def test_full_size_c2_properties(nns, oracle, torch_mod):
     dq, dr = dev(torch, s), dev(torch, r)
     index = nns.DeviceIndex(dr)
     keys8 = index.search_keys(dq, index.new_keys(m), nns.flag_overrides(q=8))
-    keys4 = index.search_keys(dq, index.new_keys(m), nns.flag_overrides(q=4))
+    keys4 = index.search_keys(dq, index.new_keys(m))
+    keys_exact = index.search_keys(dq, index.new_keys(m), nns.FLAG_EXACT_FORM)
     torch.cuda.synchronize()
     assert torch.equal(keys8, keys4)
+    assert torch.equal(keys8, keys_exact)  # screened and exact-form kernels: bit-identical (dist, idx) keys
     assert int(keys8.sum().item()) == int(keys4.sum().item())
     again = index.search_keys(dq, keys8.clone())  # idempotent: min with itself
     assert torch.equal(again, keys8)
