@@ -345,7 +345,7 @@ def main():
             x_rate = my_pairs / (x_ms * 1e-3)
             roofline["exact_form_kernel"] = {"kernel_ms": x_ms, "kernel_pairs_per_s": x_rate, "executed_lane_slots_per_pair": 2 * k,
                                              "frac": x_rate * 2.0 * k / lane_peak}
-    elif k <= 32 or True:
+    else:
         # reference-parallel kernel (k > 32 until the tensor path exists, or very few queries)
         hbm = float(pk.get("hbm_gbs", 6650.0))
         if m < 16:

@@ -281,3 +281,16 @@ def test_full_size_c2_properties(nns, oracle, torch_mod):
     assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= 255, rep
     grev = nns.DeviceIndex(torch.flip(dr, dims=[0]).contiguous()).search(dq).cpu().numpy()
     assert np.array_equal(n - 1 - grev, g)
+
+
+def test_search_multi_on_every_visible_gpu(nns, oracle, torch_mod):
+    """nns_b200_search_multi (one process, host thread per GPU): both shardings return V0's answer
+    for every GPU count; needs >= 2 visible GPUs to be more than a smoke test."""
+    ngpu = torch_mod.cuda.device_count()
+    k, m, n = 3, 5000, 300000
+    s, r = make_case("clustered", k, m, n, 1000)  # duplicates: ties must resolve to the lowest index
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    for g in sorted({1, min(2, ngpu), ngpu}):
+        for mode in (0, 1):
+            out = nns.search_multi(k, m, n, s, r, num_gpus=g, shard_mode=mode)
+            assert np.array_equal(out, v), (g, mode, int((out != v).sum()))
