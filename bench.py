@@ -345,8 +345,17 @@ def main():
             x_rate = my_pairs / (x_ms * 1e-3)
             roofline["exact_form_kernel"] = {"kernel_ms": x_ms, "kernel_pairs_per_s": x_rate, "executed_lane_slots_per_pair": 2 * k,
                                              "frac": x_rate * 2.0 * k / lane_peak}
+    elif nns_b200.plan(k, m, r1 - r0, args.flags)["path"] == 2:
+        # tcgen05 path: 2k FLOPs per pair (the -2 q.r contraction only; norms, epilogue and the exact
+        # re-score count as zero) against the measured dense BF16 peak
+        achieved = kern_pairs_per_s * 2.0 * k / 1e12
+        peak = float(pk.get("bf16_tflops", 1590.0))
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": f"{pk_src} bf16_tflops (burst, cuBLAS 8192^3)",
+                    "kernel": "tcgen05 BF16 screen (K padded to %d) + query image + exact FP32 re-score" % (64 if k <= 64 else 128),
+                    "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": nns_b200.tensor_stats()}
     else:
-        # reference-parallel kernel (k > 32 until the tensor path exists, or very few queries)
+        # reference-parallel kernel (k > 128, or very few queries)
         hbm = float(pk.get("hbm_gbs", 6650.0))
         if m < 16:
             bytes_per_launch = 4.0 * (k + 1) * (r1 - r0) + 4.0 * k * m + 8.0 * m

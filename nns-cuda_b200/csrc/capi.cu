@@ -134,8 +134,22 @@ static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn oc
     const bool exact = mode == LOWK_EXACT_V0;
     const int nblocks = ceil_div(n, LB);
     memset(p, 0, sizeof(*p));
-    if (flags & NNS_B200_FLAG_FORCE_TENSOR)
-        return fail(NNS_B200_ERR_UNSUPPORTED, "tensor path not available in this build");
+    const bool tensor_ok = k > LOWK_MAX_K && k <= TENSOR_MAX_K;
+    if ((flags & NNS_B200_FLAG_FORCE_TENSOR) && !tensor_ok)
+        return fail(NNS_B200_ERR_UNSUPPORTED, "tensor path needs %d < k <= %d", LOWK_MAX_K, TENSOR_MAX_K);
+    if (tensor_ok && !(flags & (NNS_B200_FLAG_FORCE_WIDE | NNS_B200_FLAG_FORCE_LOWK)) &&
+        ((flags & NNS_B200_FLAG_FORCE_TENSOR) || m >= 256)) {
+        // tcgen05 path: one CTA per 256-query strip x reference range (splits chosen at launch)
+        p->path = 2;
+        p->q = 1;
+        p->warps = 10;
+        p->stages = 4;
+        p->nqb = ceil_div(m, 256);
+        p->splits = 1;
+        p->bps = nblocks;
+        p->smem = 0;
+        return NNS_B200_OK;
+    }
     bool lowk = (k <= LOWK_MAX_K) && m >= 16;
     if (flags & NNS_B200_FLAG_FORCE_LOWK) {
         if (k > LOWK_MAX_K) return fail(NNS_B200_ERR_UNSUPPORTED, "low-k path needs k <= %d", LOWK_MAX_K);
@@ -233,7 +247,7 @@ struct DeviceCtx {
     std::mutex mu;  // serialises users of the cached buffers/streams of this device
     cudaStream_t compute = nullptr, copy = nullptr;
     std::vector<cudaEvent_t> events;
-    DevBuf q, r, index, keys, idx;
+    DevBuf q, r, index, keys, idx, stats;
     std::map<std::tuple<int, int, int, int, int>, int> occ_cache;
 };
 
@@ -314,6 +328,16 @@ static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_quer
     ST_TRY(make_plan(k, m, n, flags, c->num_sms, occ_query, c, &p));
     const int mode = lowk_mode_of(flags);
     const int nblocks = ceil_div(n, LB);
+    if (p.path == 2) {
+        // the tensor section (centre, |r'|^2, BF16 image) follows the FP32 blocks of the whole index
+        const float* d_section = d_blocks + (size_t)nblocks * index_block_floats(k);
+        int launches = 0;
+        ST_TRY(buf_reserve(&c->stats, 64));
+        CU_TRY(tensor_search(k, m, n, d_queries, d_blocks, d_section, index_base, d_keys, mode == LOWK_EXACT_V0,
+                             c->num_sms, st, &launches, (unsigned*)c->stats.p));
+        g_launches.fetch_add((unsigned long long)launches, std::memory_order_relaxed);
+        return NNS_B200_OK;
+    }
     if (p.path == 0) {
         LowkArgs a{};
         a.queries = d_queries; a.m = m; a.header = d_header; a.blocks = d_blocks; a.nblocks = nblocks;
@@ -380,6 +404,8 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
     // chunk = about 32 MiB of AoS reference data, a whole number of reference blocks
     long long chunk = ((32ll << 20) / ((long long)k * 4)) / LB * LB;
     if (chunk < LB) chunk = LB;
+    const bool has_tensor = tensor_section_floats(k, n) != 0;
+    if (has_tensor) chunk = ((long long)n + LB - 1) / LB * LB;  // the centre needs the whole reference set
     const int nchunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
     while ((int)c->events.size() < nchunks) {
         cudaEvent_t ev;
@@ -396,6 +422,9 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
         float* d_blocks_c = d_index + INDEX_HEADER_FLOATS + (j0 / LB) * (long long)index_block_floats(k);
         CU_TRY(launch_index_build(k, cn, d_r + j0 * k, d_index, d_blocks_c, ci == 0, c->compute));
         g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (has_tensor)
+            CU_TRY(tensor_index_build(k, cn, d_r, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(cn, LB) * index_block_floats(k),
+                                      c->compute));
         ST_TRY(search_keys_on(c, k, m, cn, d_q, d_index, d_blocks_c, index_base + (int)j0, d_keys, host_flags(),
                               c->compute));
     }
@@ -457,7 +486,7 @@ int nns_b200_shutdown(void)
         if (c->ready && cudaSetDevice(c->device) == cudaSuccess) {
             cudaStreamSynchronize(c->compute);
             cudaStreamSynchronize(c->copy);
-            for (DevBuf* b : {&c->q, &c->r, &c->index, &c->keys, &c->idx}) {
+            for (DevBuf* b : {&c->q, &c->r, &c->index, &c->keys, &c->idx, &c->stats}) {
                 if (b->p) cudaFree(b->p);
                 b->p = nullptr;
                 b->cap = 0;
@@ -477,7 +506,8 @@ int nns_b200_shutdown(void)
 size_t nns_b200_index_floats(int k, int n)
 {
     if (k <= 0 || n <= 0) return 0;
-    return (size_t)INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * (size_t)index_block_floats(k);
+    return (size_t)INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * (size_t)index_block_floats(k) +
+           tensor_section_floats(k, n);
 }
 
 int nns_b200_index_build(int k, int n, const float* d_refs_aos, float* d_index, void* stream)
@@ -486,6 +516,8 @@ int nns_b200_index_build(int k, int n, const float* d_refs_aos, float* d_index, 
     if (n > 0 && (!d_refs_aos || !d_index)) return fail(NNS_B200_ERR_INVALID, "NULL array");
     if (((uintptr_t)d_index & 15) != 0) return fail(NNS_B200_ERR_INVALID, "index must be 16-byte aligned");
     CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_index + INDEX_HEADER_FLOATS, true, (cudaStream_t)stream));
+    CU_TRY(tensor_index_build(k, n, d_refs_aos, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * index_block_floats(k),
+                              (cudaStream_t)stream));
     g_launches.fetch_add(n > 0 ? 1 : 0, std::memory_order_relaxed);
     return NNS_B200_OK;
 }
@@ -544,6 +576,7 @@ int nns_b200_search_device(int k, int m, int n, const float* d_queries, const fl
     std::lock_guard<std::mutex> lk(c->mu);
     CU_TRY(launch_keys_init(d_keys, m, st));
     CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_index + INDEX_HEADER_FLOATS, true, st));
+    CU_TRY(tensor_index_build(k, n, d_refs_aos, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * index_block_floats(k), st));
     g_launches.fetch_add(n > 0 ? 3 : 2, std::memory_order_relaxed);  // + the unpack below
     ST_TRY(search_keys_on(c, k, m, n, d_queries, d_index, d_index + INDEX_HEADER_FLOATS, 0, d_keys, flags, st));
     CU_TRY(launch_keys_unpack(d_keys, m, d_idx, nullptr, st));
@@ -638,6 +671,19 @@ void nns_b200_cudaCall(int k, int m, int n, float* s_points, float* r_points, in
         exit(1);
     }
     *results = out;
+}
+
+int nns_b200_tensor_stats(unsigned* out3)
+{
+    if (!out3) return fail(NNS_B200_ERR_INVALID, "NULL out");
+    DeviceCtx* c;
+    ST_TRY(ctx_get(-1, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    out3[0] = out3[1] = out3[2] = 0;
+    if (!c->stats.p) return NNS_B200_OK;
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(out3, c->stats.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return NNS_B200_OK;
 }
 
 int nns_b200_plan(int k, int m, int n, unsigned flags, int num_sms, int* plan)

@@ -24,8 +24,19 @@ struct WideArgs {
     int nqg;     // query groups of WIDE_QT (grid.x)
     int splits;  // grid.y
     cudaStream_t stream;
+    const int* enable = nullptr;  // optional device flag: the kernel exits immediately when it is 0
 };
 cudaError_t wide_launch(bool exact, const WideArgs& a);
+
+// tensor_search.cu -- tcgen05 path for LOWK_MAX_K < k <= TENSOR_MAX_K
+constexpr int TENSOR_MAX_K = 128;
+constexpr int TENSOR_HDR_FLOATS = 256;  // [0..127] centre, [128] max |r'|^2 bits, [129] flags
+int tensor_kp(int k);
+size_t tensor_section_floats(int k, int n);
+cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_section, cudaStream_t st);
+cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
+                          int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, int* launches,
+                          unsigned* d_stats);
 
 // lowk_inst_N.cu (N = (k-1)/2)
 cudaError_t lowk_launch_range_0(int k, int q, int mode, const LowkArgs& a, int* occ);

@@ -1,0 +1,547 @@
+// tensor_search.cu -- the k > 32 path (BASELINE config C4, k = 128): the dense contraction
+// -2 Q.R^T runs on the 5th-generation tensor cores (tcgen05.mma, BF16 operands, FP32 accumulators
+// in TMEM), a fused epilogue reduces every 128-reference tile to a per-query minimum of the
+// approximate score S~ = |r'|^2 - 2 q'.r' and emits (query, tile) candidates, and an exact FP32
+// re-score of the candidate tiles in V0's subtract-square-accumulate form (core.cu:38-43) decides
+// the answer.  The m x n score matrix never leaves TMEM.
+//
+// Exactness.  q' = fl(q - c), r' = fl(r - c) are the inputs centred on the reference mean c
+// (distances are translation invariant; centring shrinks the operands ~4x for data in [0,1]).
+// The tensor cores see bf16(-2q') and bf16(r'); E(q) bounds |S~ - S| for every reference plus the
+// gap between V0's FP32 distance and the real one (tensor_band_kernel).  A tile is a candidate
+// when its minimum S~ is within 2E of the running minimum, and is re-scored when it is within 2E
+// of the final minimum: the tile holding V0's answer always qualifies, as does every tile holding
+// an exactly tied reference, and the re-score keeps the lowest index through the packed-key
+// atomicMin.  If the candidate buffer overflows (adversarial data: e.g. all points identical) a
+// device flag makes the FP32 wide kernel redo the search -- there is no host round trip.
+//
+// Kernel structure (one CTA per 256-query strip x reference range, 10 warps):
+//   warp 0   producer: 1-D bulk copies (TMA) of the pre-swizzled BF16 images: the strip's A tile
+//            once (64 KiB), then the B tiles (32 KiB per 128 references) through a 4-stage ring
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.kind::f16 M=128 N=128 K=16, two
+//            accumulator halves (query rows 0-127 / 128-255) x double-buffered = all 512 TMEM columns;
+//            tcgen05.commit releases the B stage and publishes the accumulator
+//   warps 2-9 epilogue: one thread per query row; tcgen05.ld 32 columns at a time, add |r'|^2
+//            (staged in shared memory), FMNMX3 running minimum, candidate test
+// Operand images are K-major with the 128-byte swizzle (Swizzle<3,4,3>), written by the prep
+// kernels exactly as the UMMA shared-memory descriptors expect them, so plain bulk copies suffice
+// (no tensor maps).  SASS: UTCHMMA / LDTM / UBLKCP.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "nns_internal.h"
+
+namespace nns {
+
+constexpr int T_BM = 256;     // query rows per CTA (two M = 128 accumulator halves)
+constexpr int T_BN = 128;     // references per tile == one index block
+constexpr int T_STAGES = 4;   // B ring depth
+constexpr int T_THREADS = 320;
+constexpr int T_EPI_WARPS = 8;
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMEM helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc512(uint32_t smem_dst)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_dst) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc512(uint32_t taddr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, BF16 x BF16 -> FP32, M = 128, N = 128, K = 16
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, u64 adesc, u64 bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 128 B (64 bf16),
+// 8-row swizzle atoms 1024 B apart (stride byte offset), version 1 (Blackwell).
+__device__ __forceinline__ u64 umma_desc_sw128(uint32_t smem_addr)
+{
+    u64 d = (u64)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units, bits [0,14)
+    d |= (u64)1 << 16;                            // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (u64)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
+    d |= (u64)1 << 46;                            // descriptor version, bits [46,48)
+    d |= (u64)2 << 61;                            // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128
+constexpr uint32_t T_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// order-preserving float <-> uint (for atomicMin on possibly negative scores)
+__device__ __forceinline__ unsigned f2ord(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// byte offset of element (row, t) inside an operand image with `rows` rows:
+// [t/64][rows][128 B], 16-byte chunks XOR-swizzled with the row (Swizzle<3,4,3>)
+__device__ __forceinline__ size_t image_chunk_offset(int rows, int row, int kb, int chunk)
+{
+    return (size_t)kb * rows * 128 + (size_t)row * 128 + (size_t)((chunk ^ (row & 7)) * 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference-side preparation (part of index_build for 32 < k <= 128)
+// ---------------------------------------------------------------------------------------------
+// section header (floats): [0..127] centre, [128] max |r'|^2 (bits), [129] flags (bit 0: unusable)
+__global__ void tensor_colsum_kernel(const float* __restrict__ aos, const int n, const int k, float* __restrict__ sums)
+{
+    // grid.x blocks of 256 points; thread t < k sums its dimension over the block's points
+    const long long j0 = (long long)blockIdx.x * 256;
+    const int jn = (int)min((long long)256, n - j0);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        float s = 0.0f;
+        for (int j = 0; j < jn; ++j) s += __ldg(aos + (j0 + j) * k + t);
+        atomicAdd(sums + t, s);
+    }
+}
+
+__global__ void tensor_centre_kernel(float* __restrict__ hdr, const int n, const int k)
+{
+    const int t = threadIdx.x;
+    if (t < 128) {
+        float c = (t < k && n > 0) ? hdr[t] / (float)n : 0.0f;
+        if (!(fabsf(c) <= 1e15f)) {  // NaN / INF / huge input: the tensor path is disabled for this index
+            c = 0.0f;
+            atomicOr(reinterpret_cast<unsigned*>(hdr) + 129, 1u);
+        }
+        hdr[t] = c;
+    }
+}
+
+// one CTA per 128-reference block: BF16 image [KP/64][128][128 B] of r' = fl(r - c), FP32 |r'|^2
+__global__ void __launch_bounds__(256)
+tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k, const int KP,
+                        float* __restrict__ hdr, float* __restrict__ rnc, unsigned char* __restrict__ image)
+{
+    __shared__ float rn_part[256];
+    const long long b = blockIdx.x;
+    const int row = threadIdx.x & 127, halfsel = threadIdx.x >> 7;  // two threads per reference
+    const long long j = b * T_BN + row;
+    const bool valid = j < n;
+    unsigned char* img = image + (size_t)b * KP * T_BN * 2;
+    float rn = 0.0f;
+    bool bad = false;
+    const int chunks = KP / 8;
+    for (int ch = halfsel; ch < chunks; ch += 2) {
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int t = ch * 8 + e;
+            float x = 0.0f;
+            if (valid && t < k) {
+                x = __fsub_rn(__ldg(aos + j * k + t), hdr[t]);
+                if (!(fabsf(x) <= 1e15f)) bad = true;
+            }
+            rn = __fmaf_rn(x, x, rn);
+            v[e] = __float2bfloat16_rn(x);
+        }
+        *reinterpret_cast<uint4*>(img + image_chunk_offset(T_BN, row, ch >> 3, ch & 7)) = *reinterpret_cast<const uint4*>(v);
+    }
+    rn_part[threadIdx.x] = rn;
+    __syncthreads();
+    if (halfsel == 0) {
+        rn = rn_part[row] + rn_part[row + 128];
+        rnc[b * T_BN + row] = valid ? rn : inf_f();  // padded lanes can never be a tile minimum
+        unsigned bits = (valid && rn == rn) ? __float_as_uint(rn) : 0u;
+        bits = __reduce_max_sync(0xffffffffu, bits);
+        if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + 128, bits);
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned*>(hdr) + 129, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// query-side preparation (per search call)
+// ---------------------------------------------------------------------------------------------
+// one CTA per 256-query strip: BF16 image [KP/64][256][128 B] of -2 q', band[q] = 2 E(q),
+// approx_min[q] = +INF (ordered encoding)
+__global__ void __launch_bounds__(256)
+tensor_query_image_kernel(const float* __restrict__ queries, const int m, const int k, const int KP,
+                          const float* __restrict__ hdr, unsigned char* __restrict__ image,
+                          float* __restrict__ band, unsigned* __restrict__ approx_min)
+{
+    const int row = threadIdx.x;
+    const long long q = (long long)blockIdx.x * T_BM + row;
+    const bool valid = q < m;
+    unsigned char* img = image + (size_t)blockIdx.x * KP * T_BM * 2;
+    float qn = 0.0f;
+    for (int ch = 0; ch < KP / 8; ++ch) {
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int t = ch * 8 + e;
+            float x = 0.0f;
+            if (valid && t < k) x = __fsub_rn(__ldg(queries + q * k + t), hdr[t]);
+            qn = __fmaf_rn(x, x, qn);
+            v[e] = __float2bfloat16_rn(-2.0f * x);
+        }
+        *reinterpret_cast<uint4*>(img + image_chunk_offset(T_BM, row, ch >> 3, ch & 7)) = *reinterpret_cast<const uint4*>(v);
+    }
+    if (valid) {
+        // E(q) >= |S~ - S| + |d_V0 - D'| for every reference (see the file header):
+        //   bf16 rounding of both operands   2^-7 (1 + 2^-9) |q'| |r'|
+        //   FP32 accumulation in the MMA     K 2^-23 * 2.02 |q'| |r'|
+        //   FP32 |r'|^2                      (K+1) 2^-24 |r'|^2
+        //   centring + V0 rounding           (K+8) 2^-24 (|q'| + |r'|)^2
+        const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[128]);
+        const float a = sqrtf(qn), rmax = sqrtf(r2);
+        const float u24 = 5.9604645e-8f;
+        float E = (0.0078125f * 1.002f + (float)KP * 2.02f * 2.0f * u24) * a * rmax + (KP + 1) * u24 * r2 +
+                  (KP + 8) * u24 * (a + rmax) * (a + rmax);
+        E *= 1.05f;
+        const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[129] & 1u) != 0;  // NaN / INF / huge references
+        const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f);  // false for NaN too
+        band[q] = usable ? 2.0f * E : inf_f();
+        approx_min[q] = f2ord(inf_f());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+struct TensorCand { int q; int tile; float tmin; };
+
+template <int KP>
+__global__ void __launch_bounds__(T_THREADS, 1)
+tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
+                     const float* __restrict__ rnc, const int ntiles, const int tiles_per_split,
+                     const float* __restrict__ band, unsigned* __restrict__ approx_min,
+                     TensorCand* __restrict__ cand, unsigned* __restrict__ cand_count, const unsigned cand_cap)
+{
+    constexpr int KB = KP / 64;                    // 64-element K blocks (one 128-byte swizzle row each)
+    constexpr uint32_t A_BYTES = KB * T_BM * 128;  // 64 KiB at KP = 128
+    constexpr uint32_t B_BYTES = KB * T_BN * 128;  // 32 KiB at KP = 128
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_smem = smem;
+    unsigned char* b_smem = smem + A_BYTES;
+    float* rn_s = reinterpret_cast<float*>(smem + A_BYTES + T_STAGES * B_BYTES);  // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rn_s + 2 * T_BN);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t b_full = bar0, b_empty = bar0 + 8 * T_STAGES;
+    const uint32_t acc_full = bar0 + 8 * 2 * T_STAGES, acc_empty = acc_full + 16, a_full = acc_empty + 16;
+
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const int t0 = (int)blockIdx.y * tiles_per_split;
+    const int nt = min(ntiles, t0 + tiles_per_split) - t0;
+    if (nt <= 0) return;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_EPI_WARPS); }
+        mbar_init(a_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc512(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            mbar_arrive_expect_tx(a_full, A_BYTES);
+            bulk_g2s(smem_u32(a_smem), qimage + (size_t)blockIdx.x * A_BYTES, A_BYTES, a_full);
+            for (int t = 0; t < nt; ++t) {
+                const int s = t % T_STAGES;
+                mbar_wait(b_empty + 8 * s, (uint32_t)(((t / T_STAGES) & 1) ^ 1));
+                mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES);
+                bulk_g2s(smem_u32(b_smem + (size_t)s * B_BYTES), rimage + (size_t)(t0 + t) * B_BYTES, B_BYTES, b_full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            mbar_wait(a_full, 0);
+            for (int t = 0; t < nt; ++t) {
+                const int s = t % T_STAGES, buf = t & 1;
+                mbar_wait(acc_empty + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));  // epilogue drained this buffer
+                mbar_wait(b_full + 8 * s, (uint32_t)((t / T_STAGES) & 1));       // TMA landed this stage
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(a_smem), b_addr = smem_u32(b_smem + (size_t)s * B_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const u64 bdesc = umma_desc_sw128(b_addr + kb * (T_BN * 128) + ks * 32);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const u64 adesc = umma_desc_sw128(a_addr + kb * (T_BM * 128) + h * (128 * 128) + ks * 32);
+                            tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((kb | ks) != 0));
+                        }
+                    }
+                }
+                tc_commit(b_empty + 8 * s);      // stage free once these MMAs have read it
+                tc_commit(acc_full + 8 * buf);   // accumulator complete
+            }
+        }
+    } else {
+        // ---------------- epilogue: thread = query row ----------------
+        const int e = warp - 2;                 // 0..7
+        const int lq = warp & 3;                // TMEM lane quarter this warp may access
+        const int half = e >> 2;                // accumulator half (rows 0-127 / 128-255)
+        const int row = half * 128 + lq * 32 + lane;
+        const long long q = (long long)blockIdx.x * T_BM + row;
+        const int et = (int)threadIdx.x - 64;   // 0..255
+        const float my_band = (q < m) ? band[q] : 0.0f;
+        float run_min = inf_f();
+        for (int t = 0; t < nt; ++t) {
+            const int buf = t & 1;
+            // stage |r'|^2 of this tile (overlaps the wait for the accumulator)
+            if (et < T_BN) rn_s[buf * T_BN + et] = __ldg(rnc + (size_t)(t0 + t) * T_BN + et);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(acc_full + 8 * buf, (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((buf * 2 + half) * T_BN);
+            float tmin = inf_f();
+#pragma unroll 1
+            for (int c = 0; c < T_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                const float4* rn4 = reinterpret_cast<const float4*>(rn_s + buf * T_BN + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 r = rn4[j];
+                    const float s0 = __uint_as_float(v[4 * j]) + r.x, s1 = __uint_as_float(v[4 * j + 1]) + r.y;
+                    const float s2 = __uint_as_float(v[4 * j + 2]) + r.z, s3 = __uint_as_float(v[4 * j + 3]) + r.w;
+                    tmin = min3(tmin, s0, s1);
+                    tmin = min3(tmin, s2, s3);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+            if (q < m && tmin <= run_min + my_band) {
+                const unsigned slot = atomicAdd(cand_count, 1u);
+                if (slot < cand_cap) {
+                    TensorCand cnd;
+                    cnd.q = (int)q; cnd.tile = t0 + t; cnd.tmin = tmin;
+                    cand[slot] = cnd;
+                }
+                run_min = fminf(run_min, tmin);
+            }
+        }
+        if (q < m && run_min < inf_f()) atomicMin(approx_min + q, f2ord(run_min));
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc512(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact re-score: one warp per candidate (query, 128-reference block)
+// ---------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+tensor_rescore_kernel(const float* __restrict__ queries, const int k, const float* __restrict__ blocks,
+                      const int index_base, const TensorCand* __restrict__ cand, const unsigned* __restrict__ cand_count,
+                      const unsigned cand_cap, const float* __restrict__ band, const unsigned* __restrict__ approx_min,
+                      u64* __restrict__ keys, int* __restrict__ overflow)
+{
+    const unsigned total = *cand_count;
+    if (total > cand_cap) {  // the wide kernel takes over (launched right after with this flag)
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+        return;
+    }
+    const int lane = (int)(threadIdx.x & 31);
+    const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned ci = wid; ci < total; ci += nw) {
+        const TensorCand c = cand[ci];
+        if (!(c.tmin <= ord2f(approx_min[c.q]) + band[c.q])) continue;
+        const float* blk = blocks + (size_t)c.tile * (k + 1) * LB + lane * 4;
+        const float* qp = queries + (size_t)c.q * k;
+        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+        for (int tb = 0; tb < k; tb += 32) {
+            const float qv = (tb + lane < k) ? __ldg(qp + tb + lane) : 0.0f;
+            const int te = min(32, k - tb);
+            for (int tt = 0; tt < te; ++tt) {
+                const float qt = __shfl_sync(0xffffffffu, qv, tt);
+                const float4 r = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(tb + tt) * LB));
+                const float e0 = qt - r.x, e1 = qt - r.y, e2 = qt - r.z, e3 = qt - r.w;
+                if (EXACT) {
+                    d0 = __fadd_rn(d0, __fmul_rn(e0, e0)); d1 = __fadd_rn(d1, __fmul_rn(e1, e1));
+                    d2 = __fadd_rn(d2, __fmul_rn(e2, e2)); d3 = __fadd_rn(d3, __fmul_rn(e3, e3));
+                } else {
+                    d0 = __fmaf_rn(e0, e0, d0); d1 = __fmaf_rn(e1, e1, d1);
+                    d2 = __fmaf_rn(e2, e2, d2); d3 = __fmaf_rn(e3, e3, d3);
+                }
+            }
+        }
+        const int j0 = index_base + c.tile * LB + lane * 4;
+        float best = inf_f();
+        int bj = 0;
+        if (d0 < best) { best = d0; bj = j0; }
+        if (d1 < best) { best = d1; bj = j0 + 1; }
+        if (d2 < best) { best = d2; bj = j0 + 2; }
+        if (d3 < best) { best = d3; bj = j0 + 3; }
+        u64 key = pack_key(best, bj);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const u64 o = __shfl_xor_sync(0xffffffffu, key, off);
+            key = o < key ? o : key;
+        }
+        if (lane == 0 && key < KEY_INIT) atomicMin(keys + c.q, key);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int tensor_kp(int k) { return k <= 64 ? 64 : 128; }
+
+size_t tensor_section_floats(int k, int n)
+{
+    if (k <= LOWK_MAX_K || k > TENSOR_MAX_K || n <= 0) return 0;
+    const size_t nblocks = (size_t)((n + LB - 1) / LB);
+    return (size_t)TENSOR_HDR_FLOATS + nblocks * LB + nblocks * (size_t)tensor_kp(k) * LB / 2;
+}
+
+cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_section, cudaStream_t st)
+{
+    if (tensor_section_floats(k, n) == 0) return cudaSuccess;
+    const int KP = tensor_kp(k);
+    const int nblocks = (n + LB - 1) / LB;
+    float* hdr = d_section;
+    float* rnc = d_section + TENSOR_HDR_FLOATS;
+    unsigned char* image = reinterpret_cast<unsigned char*>(rnc + (size_t)nblocks * LB);
+    cudaError_t e = cudaMemsetAsync(hdr, 0, TENSOR_HDR_FLOATS * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    tensor_colsum_kernel<<<(n + 255) / 256, 128, 0, st>>>(d_refs_aos, n, k, hdr);
+    tensor_centre_kernel<<<1, 128, 0, st>>>(hdr, n, k);
+    tensor_ref_image_kernel<<<nblocks, 256, 0, st>>>(d_refs_aos, n, k, KP, hdr, rnc, image);
+    return cudaGetLastError();
+}
+
+size_t tensor_smem_bytes(int KP)
+{
+    return (size_t)(KP / 64) * T_BM * 128 + (size_t)T_STAGES * (KP / 64) * T_BN * 128 + 2 * T_BN * sizeof(float) + 16 * 8 + 16;
+}
+
+// Search m queries against the n references of the index section; accumulates into keys.
+// Returns the number of kernels launched through *launches.
+cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
+                          int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, int* launches,
+                          unsigned* d_stats)
+{
+    const int KP = tensor_kp(k);
+    const int nblocks = (n + LB - 1) / LB;
+    const int strips = (m + T_BM - 1) / T_BM;
+    const float* hdr = d_section;
+    const float* rnc = d_section + TENSOR_HDR_FLOATS;
+    const unsigned char* rimage = reinterpret_cast<const unsigned char*>(rnc + (size_t)nblocks * LB);
+
+    // stream-ordered scratch: query image, band, approx_min, candidates, counters
+    const size_t qimg_bytes = (size_t)strips * T_BM * KP * 2;
+    const unsigned cand_cap = (unsigned)std::min<size_t>((size_t)m * 48 + 65536, (size_t)1 << 30);
+    const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
+    const size_t off_amin = off_band + (((size_t)m * 4 + 255) & ~(size_t)255);
+    const size_t off_cnt = off_amin + (((size_t)m * 4 + 255) & ~(size_t)255);
+    const size_t off_cand = off_cnt + 256;
+    const size_t total = off_cand + (size_t)cand_cap * sizeof(TensorCand);
+    unsigned char* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&scratch, total, st);
+    if (e != cudaSuccess) return e;
+    float* band = reinterpret_cast<float*>(scratch + off_band);
+    unsigned* amin = reinterpret_cast<unsigned*>(scratch + off_amin);
+    unsigned* cnt = reinterpret_cast<unsigned*>(scratch + off_cnt);
+    int* overflow = reinterpret_cast<int*>(cnt + 1);
+    TensorCand* cand = reinterpret_cast<TensorCand*>(scratch + off_cand);
+
+    e = cudaMemsetAsync(cnt, 0, 256, st);
+    if (e == cudaSuccess) {
+        tensor_query_image_kernel<<<strips, 256, 0, st>>>(d_queries, m, k, KP, hdr, scratch, band, amin);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        // reference splits so that strips x splits fills the SMs (one CTA per SM: ~194 KiB smem)
+        int splits = 1;
+        if (strips < 2 * num_sms) splits = std::min(nblocks, std::max(1, (2 * num_sms + strips - 1) / strips));
+        int tps = (nblocks + splits - 1) / splits;
+        splits = (nblocks + tps - 1) / tps;
+        // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
+        // CTA is resident per SM even at KP = 64
+        const size_t smem = std::max(tensor_smem_bytes(KP), (size_t)120 * 1024);
+        dim3 grid((unsigned)strips, (unsigned)splits);
+        if (KP == 64) {
+            e = cudaFuncSetAttribute(tensor_screen_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                tensor_screen_kernel<64><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, rnc, nblocks, tps, band, amin, cand, cnt, cand_cap);
+        } else {
+            e = cudaFuncSetAttribute(tensor_screen_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                tensor_screen_kernel<128><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, rnc, nblocks, tps, band, amin, cand, cnt, cand_cap);
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        const int rgrid = num_sms * 8;
+        if (exact)
+            tensor_rescore_kernel<true><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cand, cnt, cand_cap, band, amin, d_keys, overflow);
+        else
+            tensor_rescore_kernel<false><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cand, cnt, cand_cap, band, amin, d_keys, overflow);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        // overflow fallback: the wide kernel runs only if the device flag is set
+        WideArgs a{};
+        a.queries = d_queries; a.m = m; a.k = k; a.blocks = d_blocks; a.nblocks = nblocks;
+        a.nqg = (m + WIDE_QT - 1) / WIDE_QT;
+        int s = 1;
+        if (a.nqg < 4 * num_sms * 8) s = std::max(1, std::min((nblocks + 1) / 2, (4 * num_sms * 8 + a.nqg - 1) / a.nqg));
+        if (s > 65535) s = 65535;
+        a.blocks_per_split = (nblocks + s - 1) / s;
+        a.splits = (nblocks + a.blocks_per_split - 1) / a.blocks_per_split;
+        a.index_base = index_base; a.keys = d_keys; a.stream = st; a.enable = overflow;
+        e = wide_launch(exact, a);
+    }
+    if (launches) *launches = 4;
+    // diagnostics: [0] candidates emitted, [1] overflow flag, [2] candidate capacity
+    if (e == cudaSuccess && d_stats) {
+        e = cudaMemcpyAsync(d_stats, cnt, 2 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stats + 2, &cand_cap, sizeof(unsigned), cudaMemcpyHostToDevice, st);
+    }
+    cudaError_t e2 = cudaFreeAsync(scratch, st);
+    return e != cudaSuccess ? e : e2;
+}
+
+// 1 if the index section says the tensor path must not be used (non-finite / huge inputs)
+__global__ void tensor_flag_kernel(const float* hdr, int* out) { *out = (int)(reinterpret_cast<const unsigned*>(hdr)[129] & 1u); }
+
+}  // namespace nns

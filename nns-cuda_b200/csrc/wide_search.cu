@@ -19,8 +19,9 @@ template <bool EXACT>
 __global__ void __launch_bounds__(WIDE_THREADS)
 wide_search_kernel(const float* __restrict__ queries, const int m, const int k,
                    const float* __restrict__ blocks, const int nblocks, const int blocks_per_split,
-                   const int index_base, u64* __restrict__ keys)
+                   const int index_base, u64* __restrict__ keys, const int* __restrict__ enable)
 {
+    if (enable != nullptr && *enable == 0) return;  // conditional fallback launch (tensor path overflow)
     extern __shared__ __align__(16) float qs[];  // [k][WIDE_QT]
     __shared__ u64 red[WIDE_THREADS / 32][WIDE_QT];
     const int q0 = (int)blockIdx.x * WIDE_QT;
@@ -103,12 +104,12 @@ cudaError_t wide_launch(bool exact, const WideArgs& a)
         e = cudaFuncSetAttribute(wide_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         wide_search_kernel<true><<<grid, WIDE_THREADS, smem, a.stream>>>(
-            a.queries, a.m, a.k, a.blocks, a.nblocks, a.blocks_per_split, a.index_base, a.keys);
+            a.queries, a.m, a.k, a.blocks, a.nblocks, a.blocks_per_split, a.index_base, a.keys, a.enable);
     } else {
         e = cudaFuncSetAttribute(wide_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         wide_search_kernel<false><<<grid, WIDE_THREADS, smem, a.stream>>>(
-            a.queries, a.m, a.k, a.blocks, a.nblocks, a.blocks_per_split, a.index_base, a.keys);
+            a.queries, a.m, a.k, a.blocks, a.nblocks, a.blocks_per_split, a.index_base, a.keys, a.enable);
     }
     return cudaGetLastError();
 }

@@ -70,6 +70,7 @@ lib.nns_b200_keys_unpack.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void
 lib.nns_b200_workspace_bytes.argtypes = [c_int, c_int, c_int]
 lib.nns_b200_workspace_bytes.restype = c_size_t
 lib.nns_b200_search_device.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]
+lib.nns_b200_tensor_stats.argtypes = [POINTER(c_uint)]
 lib.nns_b200_plan.argtypes = [c_int, c_int, c_int, c_uint, c_int, POINTER(c_int)]
 
 
@@ -124,6 +125,12 @@ def plan(k: int, m: int, n: int, flags: int = 0, num_sms: int = 148) -> dict:
     _check(lib.nns_b200_plan(k, m, n, flags, num_sms, p))
     names = ("path", "q", "warps", "stages", "query_blocks", "splits", "blocks_per_split", "smem")
     return dict(zip(names, list(p)))
+
+
+def tensor_stats() -> dict:
+    out = (c_uint * 3)()
+    _check(lib.nns_b200_tensor_stats(out))
+    return {"candidates": int(out[0]), "overflow": int(out[1]), "capacity": int(out[2])}
 
 
 def index_floats(k: int, n: int) -> int:

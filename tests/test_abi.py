@@ -47,6 +47,10 @@ def test_index_geometry(nns):
     assert nns.index_floats(3, 128) == 32 + 4 * 128
     assert nns.index_floats(3, 129) == 32 + 2 * 4 * 128
     assert nns.index_floats(16, 16777216) == 32 + 17 * 16777216
+    # 32 < k <= 128: + tensor section (256-float header, |r'|^2 per lane, BF16 image padded to 64/128 dims)
+    assert nns.index_floats(128, 128) == 32 + 129 * 128 + 256 + 128 + 128 * 128 // 2
+    assert nns.index_floats(40, 129) == 32 + 2 * 41 * 128 + 256 + 2 * 128 + 2 * 64 * 128 // 2
+    assert nns.index_floats(129, 128) == 32 + 130 * 128
     assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= (32 + 2 * 4 * 128) * 4 + 80
 
 
@@ -82,7 +86,9 @@ def test_plan_paths(nns):
     assert (p["splits"] - 1) * p["blocks_per_split"] < 4194304 // 128  # no empty split
     assert p["blocks_per_split"] % 8 == 0  # whole tiles (k=3: 8 blocks per tile)
     assert p["smem"] <= 227 * 1024
-    assert nns.plan(128, 1024, 65536)["path"] == 1  # k > 32 -> generic kernel (until the tensor path)
+    assert nns.plan(128, 1024, 65536)["path"] == 2  # 32 < k <= 128, m >= 256 -> tcgen05 path
+    assert nns.plan(128, 100, 65536)["path"] == 1  # few queries -> reference-parallel FP32 kernel
+    assert nns.plan(200, 1024, 65536)["path"] == 1  # k > 128 -> reference-parallel FP32 kernel
     assert nns.plan(3, 1, 65536)["path"] == 1  # the reference's m = 1 shapes are reference-parallel
     assert nns.plan(3, 1, 65536, nns.FLAG_FORCE_LOWK)["path"] == 0
     assert nns.plan(3, 4096, 65536, nns.FLAG_FORCE_WIDE)["path"] == 1

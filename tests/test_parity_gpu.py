@@ -294,3 +294,75 @@ def test_search_multi_on_every_visible_gpu(nns, oracle, torch_mod):
         for mode in (0, 1):
             out = nns.search_multi(k, m, n, s, r, num_gpus=g, shard_mode=mode)
             assert np.array_equal(out, v), (g, mode, int((out != v).sum()))
+
+
+# ---- tcgen05 path (32 < k <= 128) -------------------------------------------------------------
+@pytest.mark.parametrize("k,m,n", [(128, 256, 4096), (128, 1000, 20000), (64, 700, 9000), (33, 300, 5000), (100, 513, 12345),
+                                    (128, 2048, 65536), (48, 1, 1000), (128, 5, 129)])
+def test_tensor_path_matches_v0(nns, oracle, torch_mod, k, m, n):
+    s, r = make_case("uniform", k, m, n, 77)
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING)
+    assert np.array_equal(g, v), int((g != v).sum())  # exact re-score in V0 rounding: identical
+    g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_TENSOR)
+    assert_rule(oracle, k, m, n, s, r, g, v, False)
+    st = nns.tensor_stats()
+    # the tcgen05 screen itself must be selective (not rescued by the overflow fallback): a handful
+    # of candidate tiles per query (running-minimum records + the 2E band), never the whole grid
+    ntiles = (n + 127) // 128
+    # (each of the <= ~300 reference splits of a strip emits its first tile, then records + band)
+    assert st["overflow"] == 0 and 0 < st["candidates"] <= m * min(ntiles, 340), st
+    if ntiles >= 400:
+        assert st["candidates"] <= 0.25 * m * ntiles, st
+    w = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_WIDE)
+    assert np.array_equal(g, w)  # same FP32 arithmetic decides in both paths
+
+
+@pytest.mark.parametrize("case", ["grid", "duplicates", "offset", "nan_inf", "all_identical", "scaled"])
+def test_tensor_path_adversarial(nns, oracle, torch_mod, case):
+    k, m, n = 128, 600, 30000
+    s, r = make_case("uniform", k, m, n, 5)
+    s, r = s.copy(), r.copy()
+    if case == "grid":  # coarse grid: many exact ties across tiles -> lowest index must win
+        s, r = (np.floor(s * 2) / 2).astype(np.float32), (np.floor(r * 2) / 2).astype(np.float32)
+    elif case == "duplicates":
+        r[1000:2000] = r[20000:21000]
+        s[::2] = r[(np.arange(0, m, 2) * 37) % n]
+    elif case == "offset":
+        s, r = s + 100.0, r + 100.0
+    elif case == "nan_inf":
+        r[::13] = np.nan
+        r[7, 3] = np.inf
+        s[3] = np.nan
+        s[4, 0] = np.inf
+    elif case == "all_identical":  # every tile ties: candidate overflow -> device-side fallback to the wide kernel
+        r[:] = r[0]
+    elif case == "scaled":
+        s, r = s * 1e8, r * 1e8
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING)
+    assert np.array_equal(g, v), (case, int((g != v).sum()))
+    g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_TENSOR)
+    st = nns.tensor_stats()
+    assert st["overflow"] == (1 if case == "all_identical" else 0), (case, st)
+    w = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_WIDE)
+    assert np.array_equal(g, w), (case, int((g != w).sum()))
+
+
+def test_tensor_path_through_host_abi_and_shards(nns, oracle, torch_mod):
+    k, m, n = 128, 1024, 40000
+    s, r = make_case("uniform", k, m, n, 9)
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    g = nns.cudaCall(k, m, n, s, r)  # auto path: k = 128, m >= 256 -> tensor
+    rep = oracle.check_tie_rule(k, m, n, s, r, g, v, REL_TOL)
+    assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= m - 2, rep
+    assert nns.plan(k, m, n)["path"] == 2
+    # reference shards accumulate into the same keys (each shard has its own centre / image)
+    torch = torch_mod
+    dq = dev(torch, s)
+    keys = None
+    for r0, r1 in ((20096, n), (0, 20096)):
+        idx = nns.DeviceIndex(dev(torch, r[r0:r1]), index_base=r0)
+        keys = idx.new_keys(m) if keys is None else keys
+        idx.search_keys(dq, keys, nns.FLAG_V0_ROUNDING)
+    assert np.array_equal(nns.unpack_keys(keys, m).cpu().numpy(), v)
