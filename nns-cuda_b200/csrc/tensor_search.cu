@@ -320,27 +320,40 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         const long long q = (long long)blockIdx.x * T_BM + row;
         const int et = (int)threadIdx.x - 64;   // 0..255
         const float my_band = (q < m) ? band[q] : 0.0f;
-        float run_min = inf_f();
+        // other CTAs (reference splits, earlier waves) may already have lowered this query's minimum
+        float run_min = (q < m) ? ord2f(approx_min[q]) : inf_f();
+        float rn_next = (et < T_BN) ? __ldg(rnc + (size_t)t0 * T_BN + et) : 0.0f;
         for (int t = 0; t < nt; ++t) {
             const int buf = t & 1;
-            // stage |r'|^2 of this tile (overlaps the wait for the accumulator)
-            if (et < T_BN) rn_s[buf * T_BN + et] = __ldg(rnc + (size_t)(t0 + t) * T_BN + et);
+            // stage |r'|^2 of this tile; the load for the next tile is issued now and lands while
+            // this tile is reduced, so no global latency sits on the epilogue's critical path
+            if (et < T_BN) {
+                rn_s[buf * T_BN + et] = rn_next;
+                if (t + 1 < nt) rn_next = __ldg(rnc + (size_t)(t0 + t + 1) * T_BN + et);
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(acc_full + 8 * buf, (uint32_t)((t >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((buf * 2 + half) * T_BN);
+            const ulonglong2* rn2 = reinterpret_cast<const ulonglong2*>(rn_s + buf * T_BN);
             float tmin = inf_f();
-#pragma unroll 1
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+#pragma unroll
             for (int c = 0; c < T_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c * 32, v);
-                tmem_ld_wait();
-                const float4* rn4 = reinterpret_cast<const float4*>(rn_s + buf * T_BN + c * 32);
+                tmem_ld_wait();  // chunk c has landed; fetch chunk c+1 while it is reduced
+                uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                if (c + 1 < T_BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 r = rn4[j];
-                    const float s0 = __uint_as_float(v[4 * j]) + r.x, s1 = __uint_as_float(v[4 * j + 1]) + r.y;
-                    const float s2 = __uint_as_float(v[4 * j + 2]) + r.z, s3 = __uint_as_float(v[4 * j + 3]) + r.w;
+                    const ulonglong2 r = rn2[c * 8 + j];
+                    u64 p01, p23;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "r"(cur[4 * j]), "r"(cur[4 * j + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "r"(cur[4 * j + 2]), "r"(cur[4 * j + 3]));
+                    float s0, s1, s2, s3;
+                    upk2(add2(p01, r.x), s0, s1);
+                    upk2(add2(p23, r.y), s2, s3);
                     tmin = min3(tmin, s0, s1);
                     tmin = min3(tmin, s2, s3);
                 }
@@ -355,10 +368,12 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     cnd.q = (int)q; cnd.tile = t0 + t; cnd.tmin = tmin;
                     cand[slot] = cnd;
                 }
-                run_min = fminf(run_min, tmin);
+                if (tmin < run_min) {
+                    run_min = tmin;
+                    atomicMin(approx_min + q, f2ord(run_min));
+                }
             }
         }
-        if (q < m && run_min < inf_f()) atomicMin(approx_min + q, f2ord(run_min));
     }
     tc_fence_before();
     __syncthreads();
@@ -382,42 +397,58 @@ tensor_rescore_kernel(const float* __restrict__ queries, const int k, const floa
     }
     const int lane = (int)(threadIdx.x & 31);
     const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned ci = wid; ci < total; ci += nw) {
-        const TensorCand c = cand[ci];
-        if (!(c.tmin <= ord2f(approx_min[c.q]) + band[c.q])) continue;
-        const float* blk = blocks + (size_t)c.tile * (k + 1) * LB + lane * 4;
-        const float* qp = queries + (size_t)c.q * k;
-        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
-        for (int tb = 0; tb < k; tb += 32) {
-            const float qv = (tb + lane < k) ? __ldg(qp + tb + lane) : 0.0f;
-            const int te = min(32, k - tb);
-            for (int tt = 0; tt < te; ++tt) {
-                const float qt = __shfl_sync(0xffffffffu, qv, tt);
-                const float4 r = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(tb + tt) * LB));
-                const float e0 = qt - r.x, e1 = qt - r.y, e2 = qt - r.z, e3 = qt - r.w;
-                if (EXACT) {
-                    d0 = __fadd_rn(d0, __fmul_rn(e0, e0)); d1 = __fadd_rn(d1, __fmul_rn(e1, e1));
-                    d2 = __fadd_rn(d2, __fmul_rn(e2, e2)); d3 = __fadd_rn(d3, __fmul_rn(e3, e3));
-                } else {
-                    d0 = __fmaf_rn(e0, e0, d0); d1 = __fmaf_rn(e1, e1, d1);
-                    d2 = __fmaf_rn(e2, e2, d2); d3 = __fmaf_rn(e3, e3, d3);
+    // each lane tests one candidate against the final minimum; survivors are then re-scored one at
+    // a time by the whole warp
+    for (unsigned base = wid * 32; base < total; base += nw * 32) {
+        const unsigned ci = base + lane;
+        TensorCand mine;
+        mine.q = 0; mine.tile = 0; mine.tmin = 0.0f;
+        bool live = false;
+        if (ci < total) {
+            mine = cand[ci];
+            live = mine.tmin <= ord2f(approx_min[mine.q]) + band[mine.q];
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, live);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int cq = __shfl_sync(0xffffffffu, mine.q, src);
+            const int ctile = __shfl_sync(0xffffffffu, mine.tile, src);
+            const float* blk = blocks + (size_t)ctile * (k + 1) * LB + lane * 4;
+            const float* qp = queries + (size_t)cq * k;
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            for (int tb = 0; tb < k; tb += 32) {
+                const float qv = (tb + lane < k) ? __ldg(qp + tb + lane) : 0.0f;
+                const int te = min(32, k - tb);
+#pragma unroll 4
+                for (int tt = 0; tt < te; ++tt) {
+                    const float qt = __shfl_sync(0xffffffffu, qv, tt);
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(tb + tt) * LB));
+                    const float e0 = qt - r.x, e1 = qt - r.y, e2 = qt - r.z, e3 = qt - r.w;
+                    if (EXACT) {
+                        d0 = __fadd_rn(d0, __fmul_rn(e0, e0)); d1 = __fadd_rn(d1, __fmul_rn(e1, e1));
+                        d2 = __fadd_rn(d2, __fmul_rn(e2, e2)); d3 = __fadd_rn(d3, __fmul_rn(e3, e3));
+                    } else {
+                        d0 = __fmaf_rn(e0, e0, d0); d1 = __fmaf_rn(e1, e1, d1);
+                        d2 = __fmaf_rn(e2, e2, d2); d3 = __fmaf_rn(e3, e3, d3);
+                    }
                 }
             }
-        }
-        const int j0 = index_base + c.tile * LB + lane * 4;
-        float best = inf_f();
-        int bj = 0;
-        if (d0 < best) { best = d0; bj = j0; }
-        if (d1 < best) { best = d1; bj = j0 + 1; }
-        if (d2 < best) { best = d2; bj = j0 + 2; }
-        if (d3 < best) { best = d3; bj = j0 + 3; }
-        u64 key = pack_key(best, bj);
+            const int j0 = index_base + ctile * LB + lane * 4;
+            float best = inf_f();
+            int bj = 0;
+            if (d0 < best) { best = d0; bj = j0; }
+            if (d1 < best) { best = d1; bj = j0 + 1; }
+            if (d2 < best) { best = d2; bj = j0 + 2; }
+            if (d3 < best) { best = d3; bj = j0 + 3; }
+            u64 key = pack_key(best, bj);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const u64 o = __shfl_xor_sync(0xffffffffu, key, off);
-            key = o < key ? o : key;
+            for (int off = 16; off > 0; off >>= 1) {
+                const u64 o = __shfl_xor_sync(0xffffffffu, key, off);
+                key = o < key ? o : key;
+            }
+            if (lane == 0 && key < KEY_INIT) atomicMin(keys + cq, key);
         }
-        if (lane == 0 && key < KEY_INIT) atomicMin(keys + c.q, key);
     }
 }
 
@@ -467,9 +498,16 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     const float* rnc = d_section + TENSOR_HDR_FLOATS;
     const unsigned char* rimage = reinterpret_cast<const unsigned char*>(rnc + (size_t)nblocks * LB);
 
-    // stream-ordered scratch: query image, band, approx_min, candidates, counters
+    // reference splits so that strips x splits fills the SMs (one CTA per SM: ~194 KiB smem)
+    int splits = 1;
+    if (strips < 2 * num_sms) splits = std::min(nblocks, std::max(1, (2 * num_sms + strips - 1) / strips));
+    const int tps = (nblocks + splits - 1) / splits;
+    splits = (nblocks + tps - 1) / tps;
+
+    // stream-ordered scratch: query image, band, approx_min, candidates, counters.  Every split of
+    // a strip emits at least its first tile per query, then running-minimum records + the band.
     const size_t qimg_bytes = (size_t)strips * T_BM * KP * 2;
-    const unsigned cand_cap = (unsigned)std::min<size_t>((size_t)m * 48 + 65536, (size_t)1 << 30);
+    const unsigned cand_cap = (unsigned)std::min<size_t>((size_t)m * (48 + 4 * (size_t)splits) + 65536, (size_t)1 << 30);
     const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
     const size_t off_amin = off_band + (((size_t)m * 4 + 255) & ~(size_t)255);
     const size_t off_cnt = off_amin + (((size_t)m * 4 + 255) & ~(size_t)255);
@@ -490,11 +528,6 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
-        // reference splits so that strips x splits fills the SMs (one CTA per SM: ~194 KiB smem)
-        int splits = 1;
-        if (strips < 2 * num_sms) splits = std::min(nblocks, std::max(1, (2 * num_sms + strips - 1) / strips));
-        int tps = (nblocks + splits - 1) / splits;
-        splits = (nblocks + tps - 1) / tps;
         // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
         // CTA is resident per SM even at KP = 64
         const size_t smem = std::max(tensor_smem_bytes(KP), (size_t)120 * 1024);
