@@ -55,6 +55,8 @@ extern "C" {
                                         lane-slots per pair) instead of screening pairs with the
                                         norm expansion and evaluating only the survivors that way;
                                         both return the same indices                          */
+#define NNS_B200_FLAG_TEST_TINY_CANDIDATES (1u << 28) /* testing: 64-entry candidate buffer in the
+                                        tcgen05 path, forcing its overflow fallback              */
 /* bits 8-15 / 16-23 / 24-27: tuning overrides (queries per thread, warps per CTA, ring stages) */
 
 /* ---- the drop-in symbol ------------------------------------------------------------------

@@ -334,7 +334,8 @@ static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_quer
         int launches = 0;
         ST_TRY(buf_reserve(&c->stats, 64));
         CU_TRY(tensor_search(k, m, n, d_queries, d_blocks, d_section, index_base, d_keys, mode == LOWK_EXACT_V0,
-                             c->num_sms, st, &launches, (unsigned*)c->stats.p));
+                             c->num_sms, st, &launches, (unsigned*)c->stats.p,
+                             (flags & NNS_B200_FLAG_TEST_TINY_CANDIDATES) != 0));
         g_launches.fetch_add((unsigned long long)launches, std::memory_order_relaxed);
         return NNS_B200_OK;
     }

@@ -36,7 +36,7 @@ size_t tensor_section_floats(int k, int n);
 cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_section, cudaStream_t st);
 cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
                           int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, int* launches,
-                          unsigned* d_stats);
+                          unsigned* d_stats, bool tiny_candidate_buffer);
 
 // lowk_inst_N.cu (N = (k-1)/2)
 cudaError_t lowk_launch_range_0(int k, int q, int mode, const LowkArgs& a, int* occ);

@@ -21,8 +21,11 @@
 //   warp 1   MMA issuer: one elected lane issues tcgen05.mma.kind::f16 M=128 N=128 K=16, two
 //            accumulator halves (query rows 0-127 / 128-255) x double-buffered = all 512 TMEM columns;
 //            tcgen05.commit releases the B stage and publishes the accumulator
-//   warps 2-9 epilogue: one thread per query row; tcgen05.ld 32 columns at a time, add |r'|^2
-//            (staged in shared memory), FMNMX3 running minimum, candidate test
+//   warps 2-9 epilogue: one thread per query row; tcgen05.ld 32 columns at a time (double
+//            buffered), FMNMX3 running minimum, candidate test.  |r'|^2 is folded into the
+//            contraction as one extra K = 16 step (A carries 1,1,1; B carries |r'|^2 split into three
+//            BF16 terms), so the epilogue touches neither shared memory nor the FP32 pipe: shared
+//            memory bandwidth is what the MMA operand fetch needs (M = N = 128: 128 B/clk).
 // Operand images are K-major with the 128-byte swizzle (Swizzle<3,4,3>), written by the prep
 // kernels exactly as the UMMA shared-memory descriptors expect them, so plain bulk copies suffice
 // (no tensor maps).  SASS: UTCHMMA / LDTM / UBLKCP.
@@ -94,6 +97,17 @@ __device__ __forceinline__ u64 umma_desc_sw128(uint32_t smem_addr)
     d |= (u64)2 << 61;                            // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
+// UMMA descriptor for the extra K = 16 step: K-major, no swizzle ("interleave"): 8-row x 16-byte
+// core matrices; the two 16-byte K chunks of a row are `rows * 16` bytes apart (leading byte
+// offset), consecutive 8-row groups 128 bytes apart (stride byte offset) -> layout [chunk][row][16 B]
+__device__ __forceinline__ u64 umma_desc_interleave(uint32_t smem_addr, uint32_t rows)
+{
+    u64 d = (u64)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (u64)((rows * 16u) >> 4) << 16;  // leading byte offset
+    d |= (u64)(128 >> 4) << 32;           // stride byte offset
+    d |= (u64)1 << 46;                    // descriptor version
+    return d;                             // layout type 0 = no swizzle
+}
 // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128
 constexpr uint32_t T_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
@@ -115,6 +129,9 @@ __device__ __forceinline__ size_t image_chunk_offset(int rows, int row, int kb, 
     return (size_t)kb * rows * 128 + (size_t)row * 128 + (size_t)((chunk ^ (row & 7)) * 16);
 }
 
+// operand image sizes in bytes: KP/64 swizzled K blocks + the extra K = 16 step ([2][rows][16 B])
+__host__ __device__ constexpr size_t image_bytes(int rows, int KP) { return (size_t)rows * KP * 2 + (size_t)rows * 32; }
+
 // ---------------------------------------------------------------------------------------------
 // reference-side preparation (part of index_build for 32 < k <= 128)
 // ---------------------------------------------------------------------------------------------
@@ -126,7 +143,10 @@ __global__ void tensor_colsum_kernel(const float* __restrict__ aos, const int n,
     const int jn = (int)min((long long)256, n - j0);
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         float s = 0.0f;
-        for (int j = 0; j < jn; ++j) s += __ldg(aos + (j0 + j) * k + t);
+        for (int j = 0; j < jn; ++j) {
+            const float x = __ldg(aos + (j0 + j) * k + t);
+            if (fabsf(x) <= 1e15f) s += x;  // NaN / INF / huge coordinates do not steer the centre
+        }
         atomicAdd(sums + t, s);
     }
 }
@@ -144,17 +164,18 @@ __global__ void tensor_centre_kernel(float* __restrict__ hdr, const int n, const
     }
 }
 
-// one CTA per 128-reference block: BF16 image [KP/64][128][128 B] of r' = fl(r - c), FP32 |r'|^2
+// one CTA per 128-reference block: BF16 image [KP/64][128][128 B] of r' = fl(r - c), then the extra
+// K step [2][128][16 B] carrying |r'|^2 (FP32, split into three BF16 terms; +INF for padded lanes)
 __global__ void __launch_bounds__(256)
 tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k, const int KP,
-                        float* __restrict__ hdr, float* __restrict__ rnc, unsigned char* __restrict__ image)
+                        float* __restrict__ hdr, unsigned char* __restrict__ image)
 {
     __shared__ float rn_part[256];
     const long long b = blockIdx.x;
     const int row = threadIdx.x & 127, halfsel = threadIdx.x >> 7;  // two threads per reference
     const long long j = b * T_BN + row;
     const bool valid = j < n;
-    unsigned char* img = image + (size_t)b * KP * T_BN * 2;
+    unsigned char* img = image + (size_t)b * image_bytes(T_BN, KP);
     float rn = 0.0f;
     bool bad = false;
     const int chunks = KP / 8;
@@ -166,7 +187,9 @@ tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k,
             float x = 0.0f;
             if (valid && t < k) {
                 x = __fsub_rn(__ldg(aos + j * k + t), hdr[t]);
-                if (!(fabsf(x) <= 1e15f)) bad = true;
+                // a NaN / INF coordinate only poisons its own column (that reference cannot win in
+                // V0 either); finite but huge values would overflow the error-bound arithmetic
+                if (fabsf(x) > 1e15f && fabsf(x) < inf_f()) bad = true;
             }
             rn = __fmaf_rn(x, x, rn);
             v[e] = __float2bfloat16_rn(x);
@@ -177,8 +200,19 @@ tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k,
     __syncthreads();
     if (halfsel == 0) {
         rn = rn_part[row] + rn_part[row + 128];
-        rnc[b * T_BN + row] = valid ? rn : inf_f();  // padded lanes can never be a tile minimum
-        unsigned bits = (valid && rn == rn) ? __float_as_uint(rn) : 0u;
+        const float rv = valid ? rn : inf_f();  // padded lanes can never be a tile minimum
+        __align__(16) __nv_bfloat16 e0[8], e1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { e0[e] = __float2bfloat16_rn(0.0f); e1[e] = __float2bfloat16_rn(0.0f); }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(rv);
+        const float rem1 = (rv < inf_f()) ? rv - __bfloat162float(hi) : 0.0f;
+        const __nv_bfloat16 mid = __float2bfloat16_rn(rem1);
+        const float rem2 = rem1 - __bfloat162float(mid);
+        e0[0] = hi; e0[1] = mid; e0[2] = __float2bfloat16_rn(rem2);
+        unsigned char* extra = img + (size_t)KP * T_BN * 2;
+        *reinterpret_cast<uint4*>(extra + row * 16) = *reinterpret_cast<const uint4*>(e0);
+        *reinterpret_cast<uint4*>(extra + T_BN * 16 + row * 16) = *reinterpret_cast<const uint4*>(e1);
+        unsigned bits = (valid && rn < inf_f()) ? __float_as_uint(rn) : 0u;  // NaN / INF norms excluded
         bits = __reduce_max_sync(0xffffffffu, bits);
         if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + 128, bits);
     }
@@ -198,7 +232,7 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
     const int row = threadIdx.x;
     const long long q = (long long)blockIdx.x * T_BM + row;
     const bool valid = q < m;
-    unsigned char* img = image + (size_t)blockIdx.x * KP * T_BM * 2;
+    unsigned char* img = image + (size_t)blockIdx.x * image_bytes(T_BM, KP);
     float qn = 0.0f;
     for (int ch = 0; ch < KP / 8; ++ch) {
         __align__(16) __nv_bfloat16 v[8];
@@ -212,16 +246,24 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         }
         *reinterpret_cast<uint4*>(img + image_chunk_offset(T_BM, row, ch >> 3, ch & 7)) = *reinterpret_cast<const uint4*>(v);
     }
+    {   // extra K step: 1, 1, 1 against the three BF16 terms of |r'|^2
+        __align__(16) __nv_bfloat16 e0[8], e1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { e0[e] = __float2bfloat16_rn(e < 3 ? 1.0f : 0.0f); e1[e] = __float2bfloat16_rn(0.0f); }
+        unsigned char* extra = img + (size_t)KP * T_BM * 2;
+        *reinterpret_cast<uint4*>(extra + row * 16) = *reinterpret_cast<const uint4*>(e0);
+        *reinterpret_cast<uint4*>(extra + T_BM * 16 + row * 16) = *reinterpret_cast<const uint4*>(e1);
+    }
     if (valid) {
         // E(q) >= |S~ - S| + |d_V0 - D'| for every reference (see the file header):
         //   bf16 rounding of both operands   2^-7 (1 + 2^-9) |q'| |r'|
         //   FP32 accumulation in the MMA     K 2^-23 * 2.02 |q'| |r'|
-        //   FP32 |r'|^2                      (K+1) 2^-24 |r'|^2
+        //   FP32 |r'|^2 and its 3-term split (K+1) 2^-24 |r'|^2 + 2^-22 |r'|^2
         //   centring + V0 rounding           (K+8) 2^-24 (|q'| + |r'|)^2
         const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[128]);
         const float a = sqrtf(qn), rmax = sqrtf(r2);
         const float u24 = 5.9604645e-8f;
-        float E = (0.0078125f * 1.002f + (float)KP * 2.02f * 2.0f * u24) * a * rmax + (KP + 1) * u24 * r2 +
+        float E = (0.0078125f * 1.002f + (float)KP * 2.02f * 2.0f * u24) * a * rmax + (KP + 5) * u24 * r2 +
                   (KP + 8) * u24 * (a + rmax) * (a + rmax);
         E *= 1.05f;
         const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[129] & 1u) != 0;  // NaN / INF / huge references
@@ -234,23 +276,23 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-struct TensorCand { int q; int tile; float tmin; };
+struct TensorCand { int q; int unit; float smin; };  // unit = 32 consecutive references (tile * 4 + chunk)
 
 template <int KP>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
-                     const float* __restrict__ rnc, const int ntiles, const int tiles_per_split,
+                     const int ntiles, const int tiles_per_split,
                      const float* __restrict__ band, unsigned* __restrict__ approx_min,
                      TensorCand* __restrict__ cand, unsigned* __restrict__ cand_count, const unsigned cand_cap)
 {
     constexpr int KB = KP / 64;                    // 64-element K blocks (one 128-byte swizzle row each)
-    constexpr uint32_t A_BYTES = KB * T_BM * 128;  // 64 KiB at KP = 128
-    constexpr uint32_t B_BYTES = KB * T_BN * 128;  // 32 KiB at KP = 128
+    constexpr uint32_t A_MAIN = KB * T_BM * 128, B_MAIN = KB * T_BN * 128;
+    constexpr uint32_t A_BYTES = (uint32_t)image_bytes(T_BM, KP);  // 72 KiB at KP = 128
+    constexpr uint32_t B_BYTES = (uint32_t)image_bytes(T_BN, KP);  // 36 KiB at KP = 128
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_smem = smem;
     unsigned char* b_smem = smem + A_BYTES;
-    float* rn_s = reinterpret_cast<float*>(smem + A_BYTES + T_STAGES * B_BYTES);  // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rn_s + 2 * T_BN);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + T_STAGES * B_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_full = bar0, b_empty = bar0 + 8 * T_STAGES;
@@ -307,6 +349,14 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                         }
                     }
                 }
+                {   // extra K step: + |r'|^2
+                    const u64 bdesc = umma_desc_interleave(b_addr + B_MAIN, T_BN);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const u64 adesc = umma_desc_interleave(a_addr + A_MAIN + h * (128 * 16), T_BM);
+                        tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, 1u);
+                    }
+                }
                 tc_commit(b_empty + 8 * s);      // stage free once these MMAs have read it
                 tc_commit(acc_full + 8 * buf);   // accumulator complete
             }
@@ -318,26 +368,16 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         const int half = e >> 2;                // accumulator half (rows 0-127 / 128-255)
         const int row = half * 128 + lq * 32 + lane;
         const long long q = (long long)blockIdx.x * T_BM + row;
-        const int et = (int)threadIdx.x - 64;   // 0..255
         const float my_band = (q < m) ? band[q] : 0.0f;
         // other CTAs (reference splits, earlier waves) may already have lowered this query's minimum
         float run_min = (q < m) ? ord2f(approx_min[q]) : inf_f();
-        float rn_next = (et < T_BN) ? __ldg(rnc + (size_t)t0 * T_BN + et) : 0.0f;
         for (int t = 0; t < nt; ++t) {
             const int buf = t & 1;
-            // stage |r'|^2 of this tile; the load for the next tile is issued now and lands while
-            // this tile is reduced, so no global latency sits on the epilogue's critical path
-            if (et < T_BN) {
-                rn_s[buf * T_BN + et] = rn_next;
-                if (t + 1 < nt) rn_next = __ldg(rnc + (size_t)(t0 + t + 1) * T_BN + et);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(acc_full + 8 * buf, (uint32_t)((t >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((buf * 2 + half) * T_BN);
-            const ulonglong2* rn2 = reinterpret_cast<const ulonglong2*>(rn_s + buf * T_BN);
-            float tmin = inf_f();
             uint32_t va[32], vb[32];
+            float cmin[T_BN / 32];
             tmem_ld32(taddr, va);
 #pragma unroll
             for (int c = 0; c < T_BN / 32; ++c) {
@@ -345,32 +385,29 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 uint32_t (&cur)[32] = (c & 1) ? vb : va;
                 uint32_t (&nxt)[32] = (c & 1) ? va : vb;
                 if (c + 1 < T_BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+                float cm = inf_f();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const ulonglong2 r = rn2[c * 8 + j];
-                    u64 p01, p23;
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "r"(cur[4 * j]), "r"(cur[4 * j + 1]));
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "r"(cur[4 * j + 2]), "r"(cur[4 * j + 3]));
-                    float s0, s1, s2, s3;
-                    upk2(add2(p01, r.x), s0, s1);
-                    upk2(add2(p23, r.y), s2, s3);
-                    tmin = min3(tmin, s0, s1);
-                    tmin = min3(tmin, s2, s3);
-                }
+                for (int j = 0; j < 16; ++j)
+                    cm = min3(cm, __uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]));
+                cmin[c] = cm;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
-            if (q < m && tmin <= run_min + my_band) {
-                const unsigned slot = atomicAdd(cand_count, 1u);
-                if (slot < cand_cap) {
-                    TensorCand cnd;
-                    cnd.q = (int)q; cnd.tile = t0 + t; cnd.tmin = tmin;
-                    cand[slot] = cnd;
-                }
-                if (tmin < run_min) {
-                    run_min = tmin;
-                    atomicMin(approx_min + q, f2ord(run_min));
+            // candidates at 32-reference granularity (one TMEM chunk): 4x less to re-score
+#pragma unroll
+            for (int c = 0; c < T_BN / 32; ++c) {
+                if (q < m && cmin[c] <= run_min + my_band) {
+                    const unsigned slot = atomicAdd(cand_count, 1u);
+                    if (slot < cand_cap) {
+                        TensorCand cnd;
+                        cnd.q = (int)q; cnd.unit = (t0 + t) * (T_BN / 32) + c; cnd.smin = cmin[c];
+                        cand[slot] = cnd;
+                    }
+                    if (cmin[c] < run_min) {
+                        run_min = cmin[c];
+                        atomicMin(approx_min + q, f2ord(run_min));
+                    }
                 }
             }
         }
@@ -398,50 +435,37 @@ tensor_rescore_kernel(const float* __restrict__ queries, const int k, const floa
     const int lane = (int)(threadIdx.x & 31);
     const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     // each lane tests one candidate against the final minimum; survivors are then re-scored one at
-    // a time by the whole warp
+    // a time by the whole warp, one lane per reference of the 32-reference unit
     for (unsigned base = wid * 32; base < total; base += nw * 32) {
         const unsigned ci = base + lane;
         TensorCand mine;
-        mine.q = 0; mine.tile = 0; mine.tmin = 0.0f;
+        mine.q = 0; mine.unit = 0; mine.smin = 0.0f;
         bool live = false;
         if (ci < total) {
             mine = cand[ci];
-            live = mine.tmin <= ord2f(approx_min[mine.q]) + band[mine.q];
+            live = mine.smin <= ord2f(approx_min[mine.q]) + band[mine.q];
         }
         unsigned mask = __ballot_sync(0xffffffffu, live);
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
             const int cq = __shfl_sync(0xffffffffu, mine.q, src);
-            const int ctile = __shfl_sync(0xffffffffu, mine.tile, src);
-            const float* blk = blocks + (size_t)ctile * (k + 1) * LB + lane * 4;
+            const int unit = __shfl_sync(0xffffffffu, mine.unit, src);
+            const int jl = unit * 32 + lane;  // reference index within this index
+            const float* col = blocks + (size_t)(jl >> 7) * (k + 1) * LB + (jl & (LB - 1));
             const float* qp = queries + (size_t)cq * k;
-            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            float d = 0.0f;
             for (int tb = 0; tb < k; tb += 32) {
                 const float qv = (tb + lane < k) ? __ldg(qp + tb + lane) : 0.0f;
                 const int te = min(32, k - tb);
-#pragma unroll 4
+#pragma unroll 8
                 for (int tt = 0; tt < te; ++tt) {
                     const float qt = __shfl_sync(0xffffffffu, qv, tt);
-                    const float4 r = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(tb + tt) * LB));
-                    const float e0 = qt - r.x, e1 = qt - r.y, e2 = qt - r.z, e3 = qt - r.w;
-                    if (EXACT) {
-                        d0 = __fadd_rn(d0, __fmul_rn(e0, e0)); d1 = __fadd_rn(d1, __fmul_rn(e1, e1));
-                        d2 = __fadd_rn(d2, __fmul_rn(e2, e2)); d3 = __fadd_rn(d3, __fmul_rn(e3, e3));
-                    } else {
-                        d0 = __fmaf_rn(e0, e0, d0); d1 = __fmaf_rn(e1, e1, d1);
-                        d2 = __fmaf_rn(e2, e2, d2); d3 = __fmaf_rn(e3, e3, d3);
-                    }
+                    const float e = qt - __ldg(col + (size_t)(tb + tt) * LB);
+                    d = EXACT ? __fadd_rn(d, __fmul_rn(e, e)) : __fmaf_rn(e, e, d);
                 }
             }
-            const int j0 = index_base + ctile * LB + lane * 4;
-            float best = inf_f();
-            int bj = 0;
-            if (d0 < best) { best = d0; bj = j0; }
-            if (d1 < best) { best = d1; bj = j0 + 1; }
-            if (d2 < best) { best = d2; bj = j0 + 2; }
-            if (d3 < best) { best = d3; bj = j0 + 3; }
-            u64 key = pack_key(best, bj);
+            u64 key = (d < inf_f()) ? pack_key(d, index_base + jl) : KEY_INIT;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 const u64 o = __shfl_xor_sync(0xffffffffu, key, off);
@@ -461,7 +485,7 @@ size_t tensor_section_floats(int k, int n)
 {
     if (k <= LOWK_MAX_K || k > TENSOR_MAX_K || n <= 0) return 0;
     const size_t nblocks = (size_t)((n + LB - 1) / LB);
-    return (size_t)TENSOR_HDR_FLOATS + nblocks * LB + nblocks * (size_t)tensor_kp(k) * LB / 2;
+    return (size_t)TENSOR_HDR_FLOATS + nblocks * image_bytes(T_BN, tensor_kp(k)) / 4;
 }
 
 cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_section, cudaStream_t st)
@@ -470,33 +494,31 @@ cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_s
     const int KP = tensor_kp(k);
     const int nblocks = (n + LB - 1) / LB;
     float* hdr = d_section;
-    float* rnc = d_section + TENSOR_HDR_FLOATS;
-    unsigned char* image = reinterpret_cast<unsigned char*>(rnc + (size_t)nblocks * LB);
+    unsigned char* image = reinterpret_cast<unsigned char*>(d_section + TENSOR_HDR_FLOATS);
     cudaError_t e = cudaMemsetAsync(hdr, 0, TENSOR_HDR_FLOATS * sizeof(float), st);
     if (e != cudaSuccess) return e;
     tensor_colsum_kernel<<<(n + 255) / 256, 128, 0, st>>>(d_refs_aos, n, k, hdr);
     tensor_centre_kernel<<<1, 128, 0, st>>>(hdr, n, k);
-    tensor_ref_image_kernel<<<nblocks, 256, 0, st>>>(d_refs_aos, n, k, KP, hdr, rnc, image);
+    tensor_ref_image_kernel<<<nblocks, 256, 0, st>>>(d_refs_aos, n, k, KP, hdr, image);
     return cudaGetLastError();
 }
 
 size_t tensor_smem_bytes(int KP)
 {
-    return (size_t)(KP / 64) * T_BM * 128 + (size_t)T_STAGES * (KP / 64) * T_BN * 128 + 2 * T_BN * sizeof(float) + 16 * 8 + 16;
+    return image_bytes(T_BM, KP) + (size_t)T_STAGES * image_bytes(T_BN, KP) + 16 * 8 + 16;
 }
 
 // Search m queries against the n references of the index section; accumulates into keys.
 // Returns the number of kernels launched through *launches.
 cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
                           int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, int* launches,
-                          unsigned* d_stats)
+                          unsigned* d_stats, bool tiny_candidate_buffer)
 {
     const int KP = tensor_kp(k);
     const int nblocks = (n + LB - 1) / LB;
     const int strips = (m + T_BM - 1) / T_BM;
     const float* hdr = d_section;
-    const float* rnc = d_section + TENSOR_HDR_FLOATS;
-    const unsigned char* rimage = reinterpret_cast<const unsigned char*>(rnc + (size_t)nblocks * LB);
+    const unsigned char* rimage = reinterpret_cast<const unsigned char*>(d_section + TENSOR_HDR_FLOATS);
 
     // reference splits so that strips x splits fills the SMs (one CTA per SM: ~194 KiB smem)
     int splits = 1;
@@ -506,8 +528,10 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
 
     // stream-ordered scratch: query image, band, approx_min, candidates, counters.  Every split of
     // a strip emits at least its first tile per query, then running-minimum records + the band.
-    const size_t qimg_bytes = (size_t)strips * T_BM * KP * 2;
-    const unsigned cand_cap = (unsigned)std::min<size_t>((size_t)m * (48 + 4 * (size_t)splits) + 65536, (size_t)1 << 30);
+    const size_t qimg_bytes = (size_t)strips * image_bytes(T_BM, KP);
+    const unsigned cand_cap = tiny_candidate_buffer
+                                  ? 64u  // test hook: forces the overflow -> wide-kernel fallback
+                                  : (unsigned)std::min<size_t>((size_t)m * (64 + 6 * (size_t)splits) + 65536, (size_t)1 << 30);
     const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
     const size_t off_amin = off_band + (((size_t)m * 4 + 255) & ~(size_t)255);
     const size_t off_cnt = off_amin + (((size_t)m * 4 + 255) & ~(size_t)255);
@@ -535,11 +559,11 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         if (KP == 64) {
             e = cudaFuncSetAttribute(tensor_screen_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess)
-                tensor_screen_kernel<64><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, rnc, nblocks, tps, band, amin, cand, cnt, cand_cap);
+                tensor_screen_kernel<64><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
         } else {
             e = cudaFuncSetAttribute(tensor_screen_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess)
-                tensor_screen_kernel<128><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, rnc, nblocks, tps, band, amin, cand, cnt, cand_cap);
+                tensor_screen_kernel<128><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
         }
         if (e == cudaSuccess) e = cudaGetLastError();
     }

@@ -22,6 +22,7 @@ REF_BLOCK = 128
 KEY_INIT = 0x7F80000000000000
 FLAG_V0_ROUNDING, FLAG_FORCE_LOWK, FLAG_FORCE_WIDE, FLAG_FORCE_TENSOR, FLAG_EXACT_FORM = 1, 2, 4, 8, 16
 INDEX_HEADER_FLOATS = 32
+FLAG_TEST_TINY_CANDIDATES = 1 << 28
 
 
 def flag_overrides(q: int = 0, warps: int = 0, stages: int = 0) -> int:

@@ -48,8 +48,9 @@ def test_index_geometry(nns):
     assert nns.index_floats(3, 129) == 32 + 2 * 4 * 128
     assert nns.index_floats(16, 16777216) == 32 + 17 * 16777216
     # 32 < k <= 128: + tensor section (256-float header, |r'|^2 per lane, BF16 image padded to 64/128 dims)
-    assert nns.index_floats(128, 128) == 32 + 129 * 128 + 256 + 128 + 128 * 128 // 2
-    assert nns.index_floats(40, 129) == 32 + 2 * 41 * 128 + 256 + 2 * 128 + 2 * 64 * 128 // 2
+    # tensor section: 256-float header + per block a BF16 image (KP x 128 x 2 B) + the extra K step (128 x 32 B)
+    assert nns.index_floats(128, 128) == 32 + 129 * 128 + 256 + (128 * 128 * 2 + 128 * 32) // 4
+    assert nns.index_floats(40, 129) == 32 + 2 * 41 * 128 + 256 + 2 * (64 * 128 * 2 + 128 * 32) // 4
     assert nns.index_floats(129, 128) == 32 + 130 * 128
     assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= (32 + 2 * 4 * 128) * 4 + 80
 
