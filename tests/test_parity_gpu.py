@@ -344,7 +344,8 @@ def test_tensor_path_adversarial(nns, oracle, torch_mod, case):
     assert np.array_equal(g, v), (case, int((g != v).sum()))
     g = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_TENSOR)
     st = nns.tensor_stats()
-    assert st["overflow"] == 0, (case, st)
+    if case != "all_identical":  # there every 32-reference unit ties: the buffer may overflow (fallback is exact too)
+        assert st["overflow"] == 0, (case, st)
     w = gpu_search(nns, torch_mod, s, r, nns.FLAG_FORCE_WIDE)
     assert np.array_equal(g, w), (case, int((g != w).sum()))
     # candidate-buffer overflow: a device flag makes the FP32 wide kernel redo the search
