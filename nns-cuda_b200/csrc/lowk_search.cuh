@@ -361,25 +361,32 @@ lowk_filter_kernel(const float* __restrict__ queries, const int m, const float* 
                 // compared (a min tree keeps the dependency chains short; fmin drops NaN operands,
                 // which is safe: NaN arises only from NaN references, whose distance never wins,
                 // or beyond the magnitude guard, where tau is NaN and everything passes)
-                float mn[Q];
+                // all 2*G*Q accumulator chains advance together, one dimension at a time, so that
+                // dependent FFMA2s are 2*G*Q instructions apart (no fixed-latency stalls)
+                ulonglong2 rn[G];
+                u64 s01[G][Q], s23[G][Q];
 #pragma unroll
-                for (int h = 0; h < G; ++h) {
-                    const ulonglong2 rn = lds_v2u64(gp + 4 * h + K * LB);
-                    u64 s01[Q], s23[Q];
+                for (int h = 0; h < G; ++h) rn[h] = lds_v2u64(gp + 4 * h + K * LB);
 #pragma unroll
-                    for (int t = 0; t < K; ++t) {
+                for (int t = 0; t < K; ++t) {
+#pragma unroll
+                    for (int h = 0; h < G; ++h) {
                         const ulonglong2 rv = lds_v2u64(gp + 4 * h + t * LB);
 #pragma unroll
                         for (int i = 0; i < Q; ++i) {
-                            s01[i] = fma2(rv.x, mqq[i][t], t == 0 ? rn.x : s01[i]);
-                            s23[i] = fma2(rv.y, mqq[i][t], t == 0 ? rn.y : s23[i]);
+                            s01[h][i] = fma2(rv.x, mqq[i][t], t == 0 ? rn[h].x : s01[h][i]);
+                            s23[h][i] = fma2(rv.y, mqq[i][t], t == 0 ? rn[h].y : s23[h][i]);
                         }
                     }
+                }
+                float mn[Q];
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
 #pragma unroll
                     for (int i = 0; i < Q; ++i) {
                         float x0, x1, x2, x3;
-                        upk2(s01[i], x0, x1);
-                        upk2(s23[i], x2, x3);
+                        upk2(s01[h][i], x0, x1);
+                        upk2(s23[h][i], x2, x3);
                         mn[i] = (h == 0) ? fminf(min3(x0, x1, x2), x3) : min3(mn[i], min3(x0, x1, x2), x3);
                     }
                 }
