@@ -197,6 +197,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--shard", default=None, choices=["query", "reference"])
+    ap.add_argument("--strong", action="store_true",
+                    help="query-sharded: split the workload's m queries across the ranks (the configuration as "
+                         "BASELINE.json names it for C4/C5) instead of m queries per rank (weak scaling)")
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="nns_b200 flags word (tuning overrides)")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -231,7 +234,15 @@ def main():
         shard = "query"
 
     # ---- inputs: synthetic, generated on the host, resident in HBM before the timed region ----
-    kk, mm, nn, s_host, r_host = make_inputs(name, rank if shard == "query" else 0)
+    strong_q = args.strong and shard == "query" and world > 1
+    kk, mm, nn, s_host, r_host = make_inputs(name, rank if (shard == "query" and not strong_q) else 0)
+    m_total = m
+    if strong_q:
+        from nns_b200 import sharding
+
+        q0, q1 = sharding.query_shard(m, world, rank)
+        s_host = np.ascontiguousarray(s_host[q0:q1])
+        m = q1 - q0
     if shard == "reference":
         blocks = (n + 127) // 128
         per = ((blocks + world - 1) // world) * 128
@@ -297,9 +308,10 @@ def main():
     ms_per_step = total_ms / args.steps
     kern_ms_avg = kern_total_ms / args.steps
 
-    pairs_per_step = float(m) * float(n) * (world if shard == "query" else 1)
+    job_queries = m_total * (world if (shard == "query" and not strong_q) else 1)
+    pairs_per_step = float(job_queries) * float(n)
     value = pairs_per_step / (ms_per_step * 1e-3)
-    queries_per_s = (m * (world if shard == "query" else 1)) / (ms_per_step * 1e-3)
+    queries_per_s = job_queries / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (lowk/wide search): FP32 pipe, SURVEY 8(d) ----
     pk, pk_src = peaks()
@@ -373,8 +385,8 @@ def main():
         "metric": "pair_dist_evals_per_s", "value": value, "unit": "pairs/s", "queries_per_s": queries_per_s,
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak" if shard == "query" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(name, n_gpus, f"{shard}-sharded x{world}" + (" + NCCL MIN all-reduce of packed keys" if (shard == "reference" and world > 1) else " (no data-path collective)"),
+        "scaling": "weak" if (shard == "query" and not strong_q) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(name, n_gpus, f"{shard}-sharded x{world}" + (" + NCCL MIN all-reduce of packed keys" if (shard == "reference" and world > 1) else " (no data-path collective)") + (f", {m} of {m_total} queries per GPU" if strong_q else ""),
                                   "flushed (256 MiB write) between timed steps"),
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         "plan": nns_b200.plan(k, m, r1 - r0, args.flags),
