@@ -56,6 +56,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_traffic(workload, path_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    committed ncu --set full captures (profiles/r1_traffic.json); None when no capture matches."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return t.get(f"{workload}:{path_name}")
+    except Exception:
+        return None
+
+
 def make_inputs(name, rank=0):
     from nns_b200 import datagen
 
@@ -381,6 +391,11 @@ def main():
                         "executed_lane_slots_per_pair": 2 * k, "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s,
                         "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz"}
 
+    if world == 1:
+        pname = {0: "lowk", 1: "wide", 2: "tensor"}[nns_b200.plan(k, m, r1 - r0, args.flags)["path"]]
+        if args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING):
+            pname += "_exact"
+        roofline["traffic"] = ncu_traffic(name, pname)
     line = {
         "metric": "pair_dist_evals_per_s", "value": value, "unit": "pairs/s", "queries_per_s": queries_per_s,
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

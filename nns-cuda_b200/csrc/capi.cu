@@ -247,7 +247,7 @@ struct DeviceCtx {
     std::mutex mu;  // serialises users of the cached buffers/streams of this device
     cudaStream_t compute = nullptr, copy = nullptr;
     std::vector<cudaEvent_t> events;
-    DevBuf q, r, index, keys, idx, stats;
+    DevBuf q, r, index, keys, idx, stats, peer_keys;
     std::map<std::tuple<int, int, int, int, int>, int> occ_cache;
 };
 
@@ -379,7 +379,7 @@ static unsigned host_flags();
 // index build + search of chunk c (compute stream); every chunk accumulates into the same
 // packed keys with its own index base.
 static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, const float* r, int index_base,
-                          u64* h_keys, int* h_idx)
+                          u64* h_keys, int* h_idx, u64* ext_keys = nullptr)
 {
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard guard;
@@ -395,6 +395,9 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
     float* d_q = (float*)c->q.p;
     float* d_r = (float*)c->r.p;
     float* d_index = (float*)c->index.p;
+    // ext_keys: an already initialised key array, possibly in a PEER GPU's memory (NVLink P2P).
+    // The search accumulates into this GPU's own keys; one merge kernel then atomicMin's them
+    // into ext_keys, i.e. the cross-GPU (dist, idx) reduction is m device-side atomics over NVLink.
     u64* d_keys = (u64*)c->keys.p;
     int* d_idx = (int*)c->idx.p;
 
@@ -428,6 +431,10 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
                                       c->compute));
         ST_TRY(search_keys_on(c, k, m, cn, d_q, d_index, d_blocks_c, index_base + (int)j0, d_keys, host_flags(),
                               c->compute));
+    }
+    if (ext_keys) {
+        CU_TRY(launch_keys_merge(ext_keys, d_keys, m, c->compute));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (h_keys) {
         CU_TRY(cudaMemcpyAsync(h_keys, d_keys, (size_t)m * sizeof(u64), cudaMemcpyDeviceToHost, c->compute));
@@ -487,7 +494,7 @@ int nns_b200_shutdown(void)
         if (c->ready && cudaSetDevice(c->device) == cudaSuccess) {
             cudaStreamSynchronize(c->compute);
             cudaStreamSynchronize(c->copy);
-            for (DevBuf* b : {&c->q, &c->r, &c->index, &c->keys, &c->idx, &c->stats}) {
+            for (DevBuf* b : {&c->q, &c->r, &c->index, &c->keys, &c->idx, &c->stats, &c->peer_keys}) {
                 if (b->p) cudaFree(b->p);
                 b->p = nullptr;
                 b->cap = 0;
@@ -629,6 +636,62 @@ int nns_b200_search_multi(int k, int m, int n, const float* s_points, const floa
         // (core.cu:781-791 without the <= 0 tail defect D9); packed keys merged by integer MIN
         const long long blocks = ceil_div(n, LB);
         const long long per_blocks = (blocks + G - 1) / G;
+        // Reduction over NVLink peer memory: when every GPU can address GPU 0's memory, each GPU
+        // atomicMin's its packed keys straight into ONE key array resident on GPU 0
+        // (keys_merge_kernel) -- no NCCL, no host merge.
+        bool p2p = G > 1;
+        for (int g = 1; g < G && p2p; ++g) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, g, 0) != cudaSuccess || !can) p2p = false;
+        }
+        if (p2p) {
+            int prev = 0;
+            CU_TRY(cudaGetDevice(&prev));
+            for (int g = 1; g < G; ++g) {
+                CU_TRY(cudaSetDevice(g));
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(0, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) p2p = false;
+                cudaGetLastError();
+            }
+            CU_TRY(cudaSetDevice(prev));
+        }
+        if (p2p) {
+            DeviceCtx* c0 = ctx[0];
+            u64* shared_keys = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(c0->mu);
+                DeviceGuard guard;
+                ST_TRY(guard.enter(0));
+                ST_TRY(buf_reserve(&c0->peer_keys, (size_t)m * sizeof(u64)));
+                shared_keys = (u64*)c0->peer_keys.p;
+                CU_TRY(launch_keys_init(shared_keys, m, c0->compute));
+                CU_TRY(cudaStreamSynchronize(c0->compute));
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
+            for (int g = 0; g < G; ++g) {
+                th.emplace_back([&, g]() {
+                    const long long r0 = (long long)g * per_blocks * LB;
+                    const long long rn = r0 >= n ? 0 : ((n - r0) < per_blocks * LB ? (n - r0) : per_blocks * LB);
+                    if (rn <= 0) return;
+                    status[g] = search_host_on(ctx[g], k, m, (int)rn, s_points, r_points + r0 * k, (int)r0, nullptr, nullptr,
+                                               shared_keys);
+                    if (status[g] != NNS_B200_OK) msgs[g] = g_err;
+                });
+            }
+            for (auto& t : th) t.join();
+            for (int g = 0; g < G; ++g)
+                if (status[g] != NNS_B200_OK) return fail(status[g], "gpu %d: %s", g, msgs[g].c_str());
+            std::lock_guard<std::mutex> lk(c0->mu);
+            DeviceGuard guard;
+            ST_TRY(guard.enter(0));
+            ST_TRY(buf_reserve(&c0->idx, (size_t)m * sizeof(int)));
+            CU_TRY(launch_keys_unpack(shared_keys, m, (int*)c0->idx.p, nullptr, c0->compute));
+            CU_TRY(cudaMemcpyAsync(results, c0->idx.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c0->compute));
+            CU_TRY(cudaStreamSynchronize(c0->compute));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return NNS_B200_OK;
+        }
+        // no peer access: per-GPU keys to the host, merged there
         std::vector<std::vector<u64>> keys(G);
         for (int g = 0; g < G; ++g) {
             th.emplace_back([&, g]() {

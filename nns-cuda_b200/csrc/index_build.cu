@@ -71,6 +71,23 @@ __global__ void keys_unpack_kernel(const u64* __restrict__ keys, const int m, in
     }
 }
 
+// dst[i] = min(dst[i], src[i]); dst may live in a peer GPU's memory (NVLink P2P atomics)
+__global__ void keys_merge_kernel(u64* __restrict__ dst, const u64* __restrict__ src, const int m)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) {
+        const u64 key = src[i];
+        if (key < KEY_INIT) atomicMin(dst + i, key);
+    }
+}
+
+cudaError_t launch_keys_merge(u64* d_dst, const u64* d_src, int m, cudaStream_t st)
+{
+    if (m == 0) return cudaSuccess;
+    keys_merge_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_dst, d_src, m);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_index_build(int k, int n, const float* d_refs_aos, float* d_header, float* d_blocks,
                                bool reset_header, cudaStream_t st)
 {

@@ -10,6 +10,7 @@ namespace nns {
 cudaError_t launch_index_build(int k, int n, const float* d_refs_aos, float* d_header, float* d_blocks,
                                bool reset_header, cudaStream_t st);
 cudaError_t launch_keys_init(u64* d_keys, int m, cudaStream_t st);
+cudaError_t launch_keys_merge(u64* d_dst, const u64* d_src, int m, cudaStream_t st);
 cudaError_t launch_keys_unpack(const u64* d_keys, int m, int* d_idx, float* d_dist, cudaStream_t st);
 
 // wide_search.cu
