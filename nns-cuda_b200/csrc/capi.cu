@@ -74,6 +74,10 @@ struct Plan {
     int smem;    // dynamic shared memory bytes
 };
 
+// k <= 32, m >= 256: run the split-precision tcgen05 screen instead of the FP32 screened kernel
+// (set from the B200 measurements in profiles/; both return identical indices)
+static const bool LOWK_AUTO_TENSOR = false;
+
 typedef int (*occ_fn)(void* user, int k, int q, int mode, int warps, int stages);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -134,11 +138,12 @@ static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn oc
     const bool exact = mode == LOWK_EXACT_V0;
     const int nblocks = ceil_div(n, LB);
     memset(p, 0, sizeof(*p));
-    const bool tensor_ok = k > LOWK_MAX_K && k <= TENSOR_MAX_K;
+    const bool tensor_ok = k <= TENSOR_MAX_K;
     if ((flags & NNS_B200_FLAG_FORCE_TENSOR) && !tensor_ok)
-        return fail(NNS_B200_ERR_UNSUPPORTED, "tensor path needs %d < k <= %d", LOWK_MAX_K, TENSOR_MAX_K);
+        return fail(NNS_B200_ERR_UNSUPPORTED, "tensor path needs k <= %d", TENSOR_MAX_K);
+    const bool tensor_auto = m >= 256 && (k > LOWK_MAX_K || (LOWK_AUTO_TENSOR && !(flags & NNS_B200_FLAG_EXACT_FORM)));
     if (tensor_ok && !(flags & (NNS_B200_FLAG_FORCE_WIDE | NNS_B200_FLAG_FORCE_LOWK)) &&
-        ((flags & NNS_B200_FLAG_FORCE_TENSOR) || m >= 256)) {
+        ((flags & NNS_B200_FLAG_FORCE_TENSOR) || tensor_auto)) {
         // tcgen05 path: one CTA per 256-query strip x reference range (splits chosen at launch)
         p->path = 2;
         p->q = 1;

@@ -29,8 +29,9 @@ struct WideArgs {
 };
 cudaError_t wide_launch(bool exact, const WideArgs& a);
 
-// tensor_search.cu -- tcgen05 path for LOWK_MAX_K < k <= TENSOR_MAX_K
+// tensor_search.cu -- tcgen05 path for k <= TENSOR_MAX_K (split-precision BF16 up to TENSOR_SPLIT_MAX_K)
 constexpr int TENSOR_MAX_K = 128;
+constexpr int TENSOR_SPLIT_MAX_K = 42;  // 3k <= 128 contraction columns
 constexpr int TENSOR_HDR_FLOATS = 256;  // [0..127] centre, [128] max |r'|^2 bits, [129] flags
 int tensor_kp(int k);
 size_t tensor_section_floats(int k, int n);

@@ -132,6 +132,29 @@ __device__ __forceinline__ size_t image_chunk_offset(int rows, int row, int kb, 
 // operand image sizes in bytes: KP/64 swizzled K blocks + the extra K = 16 step ([2][rows][16 B])
 __host__ __device__ constexpr size_t image_bytes(int rows, int KP) { return (size_t)rows * KP * 2 + (size_t)rows * 32; }
 
+// Split precision (k <= TENSOR_SPLIT_MAX_K).  BF16 keeps 8 significant bits; splitting each centred
+// coordinate into hi = bf16(x) and lo = bf16(x - hi) and laying the contraction dimension out as
+//     queries:    [ qh (k) | qh (k) | ql (k) ]        references: [ rh (k) | rl (k) | rh (k) ]
+// makes one BF16 MMA pass accumulate qh.rh + qh.rl + ql.rh, i.e. q'.r' up to terms of relative size
+// ~3 * 2^-18: the screen's error bound E shrinks ~250x, so that it is selective even for k = 3 with
+// millions of references (nearest-neighbour distances ~1e-5 of the data extent).
+__host__ __device__ constexpr bool tensor_split(int k) { return k <= TENSOR_SPLIT_MAX_K; }
+// source dimension and part (0 = hi, 1 = lo) of image column `col`; dimension -1 = zero padding
+__device__ __forceinline__ void image_column(int k, int col, bool query, int& dim, int& part)
+{
+    if (!tensor_split(k)) { dim = col < k ? col : -1; part = 0; return; }
+    const int seg = col / k;
+    dim = seg < 3 ? col - seg * k : -1;
+    part = query ? (seg == 2 ? 1 : 0) : (seg == 1 ? 1 : 0);
+}
+__device__ __forceinline__ __nv_bfloat16 bf16_part(float x, int part)
+{
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    if (part == 0) return hi;
+    const float rem = x - __bfloat162float(hi);  // exact in FP32
+    return __float2bfloat16_rn((fabsf(x) < inf_f()) ? rem : 0.0f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // reference-side preparation (part of index_build for 32 < k <= 128)
 // ---------------------------------------------------------------------------------------------
@@ -183,16 +206,17 @@ tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k,
         __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int t = ch * 8 + e;
+            int dim, part;
+            image_column(k, ch * 8 + e, false, dim, part);
             float x = 0.0f;
-            if (valid && t < k) {
-                x = __fsub_rn(__ldg(aos + j * k + t), hdr[t]);
+            if (valid && dim >= 0) {
+                x = __fsub_rn(__ldg(aos + j * k + dim), hdr[dim]);
                 // a NaN / INF coordinate only poisons its own column (that reference cannot win in
                 // V0 either); finite but huge values would overflow the error-bound arithmetic
                 if (fabsf(x) > 1e15f && fabsf(x) < inf_f()) bad = true;
             }
-            rn = __fmaf_rn(x, x, rn);
-            v[e] = __float2bfloat16_rn(x);
+            if (ch * 8 + e < k) rn = __fmaf_rn(x, x, rn);  // |r'|^2 from the first copy of each dimension
+            v[e] = bf16_part(x, part);
         }
         *reinterpret_cast<uint4*>(img + image_chunk_offset(T_BN, row, ch >> 3, ch & 7)) = *reinterpret_cast<const uint4*>(v);
     }
@@ -238,11 +262,12 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int t = ch * 8 + e;
+            int dim, part;
+            image_column(k, ch * 8 + e, true, dim, part);
             float x = 0.0f;
-            if (valid && t < k) x = __fsub_rn(__ldg(queries + q * k + t), hdr[t]);
-            qn = __fmaf_rn(x, x, qn);
-            v[e] = __float2bfloat16_rn(-2.0f * x);
+            if (valid && dim >= 0) x = __fsub_rn(__ldg(queries + q * k + dim), hdr[dim]);
+            if (ch * 8 + e < k) qn = __fmaf_rn(x, x, qn);
+            v[e] = bf16_part(-2.0f * x, part);
         }
         *reinterpret_cast<uint4*>(img + image_chunk_offset(T_BM, row, ch >> 3, ch & 7)) = *reinterpret_cast<const uint4*>(v);
     }
@@ -263,7 +288,11 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[128]);
         const float a = sqrtf(qn), rmax = sqrtf(r2);
         const float u24 = 5.9604645e-8f;
-        float E = (0.0078125f * 1.002f + (float)KP * 2.02f * 2.0f * u24) * a * rmax + (KP + 5) * u24 * r2 +
+        // operand rounding: plain BF16 2^-7 (1 + 2^-9) |q'||r'|; split precision drops only
+        // ql.rl and the second-order remainders: 2 * 3.1 * 2^-18 |q'||r'|.  The MMA's FP32
+        // accumulation is charged 2^-21 per term (truncating adders).
+        const float c_round = tensor_split(k) ? 6.2f * 3.8146973e-6f : 0.0078125f * 1.002f;
+        float E = (c_round + (float)(KP + 16) * 2.04f * 4.7683716e-7f) * a * rmax + (KP + 5) * u24 * r2 +
                   (KP + 8) * u24 * (a + rmax) * (a + rmax);
         E *= 1.05f;
         const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[129] & 1u) != 0;  // NaN / INF / huge references
@@ -385,11 +414,23 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 uint32_t (&cur)[32] = (c & 1) ? vb : va;
                 uint32_t (&nxt)[32] = (c & 1) ? va : vb;
                 if (c + 1 < T_BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
-                float cm = inf_f();
+                // four independent FMNMX3 chains (depth 4) + a 2-level combine instead of one chain of 16
+                float c0 = min3(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]));
+                float c1 = min3(__uint_as_float(cur[8]), __uint_as_float(cur[9]), __uint_as_float(cur[10]));
+                float c2 = min3(__uint_as_float(cur[16]), __uint_as_float(cur[17]), __uint_as_float(cur[18]));
+                float c3 = min3(__uint_as_float(cur[24]), __uint_as_float(cur[25]), __uint_as_float(cur[26]));
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    cm = min3(cm, __uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1]));
-                cmin[c] = cm;
+                for (int j = 0; j < 2; ++j) {
+                    c0 = min3(c0, __uint_as_float(cur[3 + 2 * j]), __uint_as_float(cur[4 + 2 * j]));
+                    c1 = min3(c1, __uint_as_float(cur[11 + 2 * j]), __uint_as_float(cur[12 + 2 * j]));
+                    c2 = min3(c2, __uint_as_float(cur[19 + 2 * j]), __uint_as_float(cur[20 + 2 * j]));
+                    c3 = min3(c3, __uint_as_float(cur[27 + 2 * j]), __uint_as_float(cur[28 + 2 * j]));
+                }
+                c0 = fminf(c0, __uint_as_float(cur[7]));
+                c1 = fminf(c1, __uint_as_float(cur[15]));
+                c2 = fminf(c2, __uint_as_float(cur[23]));
+                c3 = fminf(c3, __uint_as_float(cur[31]));
+                cmin[c] = fminf(min3(c0, c1, c2), c3);
             }
             tc_fence_before();
             __syncwarp();
@@ -479,11 +520,15 @@ tensor_rescore_kernel(const float* __restrict__ queries, const int k, const floa
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int tensor_kp(int k) { return k <= 64 ? 64 : 128; }
+int tensor_kp(int k)
+{
+    const int cols = tensor_split(k) ? 3 * k : k;
+    return cols <= 64 ? 64 : 128;
+}
 
 size_t tensor_section_floats(int k, int n)
 {
-    if (k <= LOWK_MAX_K || k > TENSOR_MAX_K || n <= 0) return 0;
+    if (k < 1 || k > TENSOR_MAX_K || n <= 0) return 0;
     const size_t nblocks = (size_t)((n + LB - 1) / LB);
     return (size_t)TENSOR_HDR_FLOATS + nblocks * image_bytes(T_BN, tensor_kp(k)) / 4;
 }
@@ -520,9 +565,20 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     const float* hdr = d_section;
     const unsigned char* rimage = reinterpret_cast<const unsigned char*>(d_section + TENSOR_HDR_FLOATS);
 
-    // reference splits so that strips x splits fills the SMs (one CTA per SM: ~194 KiB smem)
+    // reference splits: minimise (waves of one CTA per SM) x (tiles per CTA); every extra split
+    // costs each query one more seed candidate, so ties go to fewer splits
     int splits = 1;
-    if (strips < 2 * num_sms) splits = std::min(nblocks, std::max(1, (2 * num_sms + strips - 1) / strips));
+    {
+        double best = 1e300;
+        const int smax = std::min(nblocks, 64);
+        for (int sp = 1; sp <= smax; ++sp) {
+            const int t = (nblocks + sp - 1) / sp;
+            const int se = (nblocks + t - 1) / t;
+            const double waves = (double)(((long long)strips * se + num_sms - 1) / num_sms);
+            const double cost = waves * ((double)t + 24.0);  // + per-CTA prologue (A tile, TMEM alloc) in tile units
+            if (cost < best * 0.97) { best = cost; splits = se; }
+        }
+    }
     const int tps = (nblocks + splits - 1) / splits;
     splits = (nblocks + tps - 1) / tps;
 

@@ -43,15 +43,19 @@ def test_header_constants_match_binding(nns):
 def test_index_geometry(nns):
     # 32-float header + (k coordinate rows + 1 norm row) x 128 lanes per block of 128 points
     assert nns.index_floats(3, 0) == 0
-    assert nns.index_floats(3, 1) == 32 + 4 * 128
-    assert nns.index_floats(3, 128) == 32 + 4 * 128
-    assert nns.index_floats(3, 129) == 32 + 2 * 4 * 128
-    assert nns.index_floats(16, 16777216) == 32 + 17 * 16777216
+    ts = lambda kp, nb: 256 + nb * (kp * 128 * 2 + 128 * 32) // 4  # tensor section (k <= 128)
+    assert nns.index_floats(3, 1) == 32 + 4 * 128 + ts(64, 1)
+    assert nns.index_floats(3, 129) == 32 + 2 * 4 * 128 + ts(64, 2)
+    assert nns.index_floats(16, 16777216) == 32 + 17 * 16777216 + ts(64, 131072)
     # 32 < k <= 128: + tensor section (256-float header, |r'|^2 per lane, BF16 image padded to 64/128 dims)
     # tensor section: 256-float header + per block a BF16 image (KP x 128 x 2 B) + the extra K step (128 x 32 B)
     assert nns.index_floats(128, 128) == 32 + 129 * 128 + 256 + (128 * 128 * 2 + 128 * 32) // 4
-    assert nns.index_floats(40, 129) == 32 + 2 * 41 * 128 + 256 + 2 * (64 * 128 * 2 + 128 * 32) // 4
+    assert nns.index_floats(40, 129) == 32 + 2 * 41 * 128 + 256 + 2 * (128 * 128 * 2 + 128 * 32) // 4  # split: 120 columns
+    assert nns.index_floats(50, 129) == 32 + 2 * 51 * 128 + 256 + 2 * (64 * 128 * 2 + 128 * 32) // 4  # plain BF16: 50 columns
     assert nns.index_floats(129, 128) == 32 + 130 * 128
+    # k <= 42: split-precision image, 3k columns padded to 64 / 128
+    assert nns.index_floats(3, 128) == 32 + 4 * 128 + 256 + (64 * 128 * 2 + 128 * 32) // 4
+    assert nns.index_floats(22, 128) == 32 + 23 * 128 + 256 + (128 * 128 * 2 + 128 * 32) // 4
     assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= (32 + 2 * 4 * 128) * 4 + 80
 
 
