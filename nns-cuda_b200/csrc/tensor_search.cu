@@ -39,7 +39,7 @@ namespace nns {
 
 constexpr int T_BM = 256;     // query rows per CTA (two M = 128 accumulator halves)
 constexpr int T_BN = 128;     // references per tile == one index block
-constexpr int T_STAGES = 4;   // B ring depth
+constexpr int T_MAX_STAGES = 24;  // B ring depth is chosen per geometry: small tiles need a deep ring to cover the TMA latency
 constexpr int T_THREADS = 320;
 constexpr int T_EPI_WARPS = 8;
 
@@ -129,8 +129,32 @@ __device__ __forceinline__ size_t image_chunk_offset(int rows, int row, int kb, 
     return (size_t)kb * rows * 128 + (size_t)row * 128 + (size_t)((chunk ^ (row & 7)) * 16);
 }
 
-// operand image sizes in bytes: KP/64 swizzled K blocks + the extra K = 16 step ([2][rows][16 B])
-__host__ __device__ constexpr size_t image_bytes(int rows, int KP) { return (size_t)rows * KP * 2 + (size_t)rows * 32; }
+// Operand image geometry.  The contraction dimension is laid out as KB blocks of 64 columns in the
+// K-major 128-byte-swizzle layout ([KB][rows][128 B]) followed by KS steps of 16 columns in the
+// K-major no-swizzle ("interleave") layout ([2*KS][rows][16 B]); `norm_col` is the first of the
+// three columns that carry |r'|^2 (references) / 1 (queries).  Small k needs no swizzled block at
+// all: for k <= 4 the 3k split-precision columns and the norm fit ONE K = 16 MMA step.
+struct TensorGeom {
+    int KB, KS, norm_col, ndata, split;
+};
+__host__ __device__ inline TensorGeom tensor_geom(int k)
+{
+    TensorGeom g;
+    g.split = k <= TENSOR_SPLIT_MAX_K ? 1 : 0;
+    g.ndata = g.split ? 3 * k : k;
+    if (g.ndata + 3 <= 16) { g.KB = 0; g.KS = 1; g.norm_col = g.ndata; }
+    else if (g.ndata + 3 <= 32) { g.KB = 0; g.KS = 2; g.norm_col = g.ndata; }
+    else if (g.ndata <= 64) { g.KB = 1; g.KS = 1; g.norm_col = 64; }
+    else { g.KB = 2; g.KS = 1; g.norm_col = 128; }
+    return g;
+}
+__host__ __device__ constexpr size_t image_bytes(int rows, int KB, int KS) { return (size_t)rows * (KB * 128 + KS * 32); }
+// byte offset of the 16-byte chunk holding columns [8*chunk, 8*chunk + 8) of `row`
+__device__ __forceinline__ size_t image_chunk_at(int rows, int KB, int row, int chunk)
+{
+    if (chunk < KB * 8) return image_chunk_offset(rows, row, chunk >> 3, chunk & 7);
+    return (size_t)KB * rows * 128 + (size_t)(chunk - KB * 8) * rows * 16 + (size_t)row * 16;
+}
 
 // Split precision (k <= TENSOR_SPLIT_MAX_K).  BF16 keeps 8 significant bits; splitting each centred
 // coordinate into hi = bf16(x) and lo = bf16(x - hi) and laying the contraction dimension out as
@@ -139,12 +163,13 @@ __host__ __device__ constexpr size_t image_bytes(int rows, int KP) { return (siz
 // ~3 * 2^-18: the screen's error bound E shrinks ~250x, so that it is selective even for k = 3 with
 // millions of references (nearest-neighbour distances ~1e-5 of the data extent).
 __host__ __device__ constexpr bool tensor_split(int k) { return k <= TENSOR_SPLIT_MAX_K; }
-// source dimension and part (0 = hi, 1 = lo) of image column `col`; dimension -1 = zero padding
-__device__ __forceinline__ void image_column(int k, int col, bool query, int& dim, int& part)
+// source dimension and part (0 = hi, 1 = lo) of data column `col` (< ndata); dimension -1 = none
+__device__ __forceinline__ void image_column(int k, int ndata, int col, bool query, int& dim, int& part)
 {
-    if (!tensor_split(k)) { dim = col < k ? col : -1; part = 0; return; }
+    if (col >= ndata) { dim = -1; part = 0; return; }
+    if (!tensor_split(k)) { dim = col; part = 0; return; }
     const int seg = col / k;
-    dim = seg < 3 ? col - seg * k : -1;
+    dim = col - seg * k;
     part = query ? (seg == 2 ? 1 : 0) : (seg == 1 ? 1 : 0);
 }
 __device__ __forceinline__ __nv_bfloat16 bf16_part(float x, int part)
@@ -187,97 +212,94 @@ __global__ void tensor_centre_kernel(float* __restrict__ hdr, const int n, const
     }
 }
 
-// one CTA per 128-reference block: BF16 image [KP/64][128][128 B] of r' = fl(r - c), then the extra
-// K step [2][128][16 B] carrying |r'|^2 (FP32, split into three BF16 terms; +INF for padded lanes)
-__global__ void __launch_bounds__(256)
-tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k, const int KP,
+// one CTA per 128-reference block: BF16 image of r' = fl(r - c) (TensorGeom layout) with |r'|^2
+// (FP32, split into three BF16 terms; +INF for padded lanes) in columns norm_col .. norm_col + 2
+__global__ void __launch_bounds__(128)
+tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k, const TensorGeom g,
                         float* __restrict__ hdr, unsigned char* __restrict__ image)
 {
-    __shared__ float rn_part[256];
     const long long b = blockIdx.x;
-    const int row = threadIdx.x & 127, halfsel = threadIdx.x >> 7;  // two threads per reference
+    const int row = threadIdx.x;  // one thread per reference
     const long long j = b * T_BN + row;
     const bool valid = j < n;
-    unsigned char* img = image + (size_t)b * image_bytes(T_BN, KP);
+    unsigned char* img = image + (size_t)b * image_bytes(T_BN, g.KB, g.KS);
+    // |r'|^2 first (ascending dimensions), because its columns may share a chunk with data columns
     float rn = 0.0f;
     bool bad = false;
-    const int chunks = KP / 8;
-    for (int ch = halfsel; ch < chunks; ch += 2) {
+    for (int t = 0; t < k; ++t) {
+        float x = 0.0f;
+        if (valid) {
+            x = __fsub_rn(__ldg(aos + j * k + t), hdr[t]);
+            // a NaN / INF coordinate only poisons its own column (that reference cannot win in
+            // V0 either); finite but huge values would overflow the error-bound arithmetic
+            if (fabsf(x) > 1e15f && fabsf(x) < inf_f()) bad = true;
+        }
+        rn = __fmaf_rn(x, x, rn);
+    }
+    const float rv = valid ? rn : inf_f();  // padded lanes can never be a tile minimum
+    const __nv_bfloat16 n_hi = __float2bfloat16_rn(rv);
+    const float rem1 = (rv < inf_f()) ? rv - __bfloat162float(n_hi) : 0.0f;
+    const __nv_bfloat16 n_mid = __float2bfloat16_rn(rem1);
+    const __nv_bfloat16 n_lo = __float2bfloat16_rn(rem1 - __bfloat162float(n_mid));
+    const int chunks = g.KB * 8 + g.KS * 2;
+    for (int ch = 0; ch < chunks; ++ch) {
         __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
+            const int col = ch * 8 + e;
             int dim, part;
-            image_column(k, ch * 8 + e, false, dim, part);
+            image_column(k, g.ndata, col, false, dim, part);
             float x = 0.0f;
-            if (valid && dim >= 0) {
-                x = __fsub_rn(__ldg(aos + j * k + dim), hdr[dim]);
-                // a NaN / INF coordinate only poisons its own column (that reference cannot win in
-                // V0 either); finite but huge values would overflow the error-bound arithmetic
-                if (fabsf(x) > 1e15f && fabsf(x) < inf_f()) bad = true;
-            }
-            if (ch * 8 + e < k) rn = __fmaf_rn(x, x, rn);  // |r'|^2 from the first copy of each dimension
-            v[e] = bf16_part(x, part);
+            if (valid && dim >= 0) x = __fsub_rn(__ldg(aos + j * k + dim), hdr[dim]);
+            __nv_bfloat16 o = bf16_part(x, part);
+            if (col == g.norm_col) o = n_hi;
+            if (col == g.norm_col + 1) o = n_mid;
+            if (col == g.norm_col + 2) o = n_lo;
+            v[e] = o;
         }
-        *reinterpret_cast<uint4*>(img + image_chunk_offset(T_BN, row, ch >> 3, ch & 7)) = *reinterpret_cast<const uint4*>(v);
+        *reinterpret_cast<uint4*>(img + image_chunk_at(T_BN, g.KB, row, ch)) = *reinterpret_cast<const uint4*>(v);
     }
-    rn_part[threadIdx.x] = rn;
-    __syncthreads();
-    if (halfsel == 0) {
-        rn = rn_part[row] + rn_part[row + 128];
-        const float rv = valid ? rn : inf_f();  // padded lanes can never be a tile minimum
-        __align__(16) __nv_bfloat16 e0[8], e1[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { e0[e] = __float2bfloat16_rn(0.0f); e1[e] = __float2bfloat16_rn(0.0f); }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(rv);
-        const float rem1 = (rv < inf_f()) ? rv - __bfloat162float(hi) : 0.0f;
-        const __nv_bfloat16 mid = __float2bfloat16_rn(rem1);
-        const float rem2 = rem1 - __bfloat162float(mid);
-        e0[0] = hi; e0[1] = mid; e0[2] = __float2bfloat16_rn(rem2);
-        unsigned char* extra = img + (size_t)KP * T_BN * 2;
-        *reinterpret_cast<uint4*>(extra + row * 16) = *reinterpret_cast<const uint4*>(e0);
-        *reinterpret_cast<uint4*>(extra + T_BN * 16 + row * 16) = *reinterpret_cast<const uint4*>(e1);
-        unsigned bits = (valid && rn < inf_f()) ? __float_as_uint(rn) : 0u;  // NaN / INF norms excluded
-        bits = __reduce_max_sync(0xffffffffu, bits);
-        if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + 128, bits);
-    }
+    unsigned bits = (valid && rn < inf_f()) ? __float_as_uint(rn) : 0u;  // NaN / INF norms excluded
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + 128, bits);
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned*>(hdr) + 129, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
 // query-side preparation (per search call)
 // ---------------------------------------------------------------------------------------------
-// one CTA per 256-query strip: BF16 image [KP/64][256][128 B] of -2 q', band[q] = 2 E(q),
-// approx_min[q] = +INF (ordered encoding)
+// one CTA per 256-query strip: BF16 image of -2 q' (TensorGeom layout, 1 in the norm columns),
+// band[q] = 2 E(q), approx_min[q] = +INF (ordered encoding)
 __global__ void __launch_bounds__(256)
-tensor_query_image_kernel(const float* __restrict__ queries, const int m, const int k, const int KP,
+tensor_query_image_kernel(const float* __restrict__ queries, const int m, const int k, const TensorGeom g,
                           const float* __restrict__ hdr, unsigned char* __restrict__ image,
                           float* __restrict__ band, unsigned* __restrict__ approx_min)
 {
     const int row = threadIdx.x;
     const long long q = (long long)blockIdx.x * T_BM + row;
     const bool valid = q < m;
-    unsigned char* img = image + (size_t)blockIdx.x * image_bytes(T_BM, KP);
+    const int KP = g.KB * 64 + g.KS * 16;  // contraction length seen by the MMA
+    unsigned char* img = image + (size_t)blockIdx.x * image_bytes(T_BM, g.KB, g.KS);
     float qn = 0.0f;
-    for (int ch = 0; ch < KP / 8; ++ch) {
+    for (int t = 0; t < k; ++t) {
+        const float x = valid ? __fsub_rn(__ldg(queries + q * k + t), hdr[t]) : 0.0f;
+        qn = __fmaf_rn(x, x, qn);
+    }
+    const int chunks = g.KB * 8 + g.KS * 2;
+    for (int ch = 0; ch < chunks; ++ch) {
         __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
+            const int col = ch * 8 + e;
             int dim, part;
-            image_column(k, ch * 8 + e, true, dim, part);
+            image_column(k, g.ndata, col, true, dim, part);
             float x = 0.0f;
             if (valid && dim >= 0) x = __fsub_rn(__ldg(queries + q * k + dim), hdr[dim]);
-            if (ch * 8 + e < k) qn = __fmaf_rn(x, x, qn);
-            v[e] = bf16_part(-2.0f * x, part);
+            __nv_bfloat16 o = bf16_part(-2.0f * x, part);
+            if (col >= g.norm_col && col < g.norm_col + 3) o = __float2bfloat16_rn(1.0f);
+            v[e] = o;
         }
-        *reinterpret_cast<uint4*>(img + image_chunk_offset(T_BM, row, ch >> 3, ch & 7)) = *reinterpret_cast<const uint4*>(v);
-    }
-    {   // extra K step: 1, 1, 1 against the three BF16 terms of |r'|^2
-        __align__(16) __nv_bfloat16 e0[8], e1[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { e0[e] = __float2bfloat16_rn(e < 3 ? 1.0f : 0.0f); e1[e] = __float2bfloat16_rn(0.0f); }
-        unsigned char* extra = img + (size_t)KP * T_BM * 2;
-        *reinterpret_cast<uint4*>(extra + row * 16) = *reinterpret_cast<const uint4*>(e0);
-        *reinterpret_cast<uint4*>(extra + T_BM * 16 + row * 16) = *reinterpret_cast<const uint4*>(e1);
+        *reinterpret_cast<uint4*>(img + image_chunk_at(T_BM, g.KB, row, ch)) = *reinterpret_cast<const uint4*>(v);
     }
     if (valid) {
         // E(q) >= |S~ - S| + |d_V0 - D'| for every reference (see the file header):
@@ -292,7 +314,7 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         // ql.rl and the second-order remainders: 2 * 3.1 * 2^-18 |q'||r'|.  The MMA's FP32
         // accumulation is charged 2^-21 per term (truncating adders).
         const float c_round = tensor_split(k) ? 6.2f * 3.8146973e-6f : 0.0078125f * 1.002f;
-        float E = (c_round + (float)(KP + 16) * 2.04f * 4.7683716e-7f) * a * rmax + (KP + 5) * u24 * r2 +
+        float E = (c_round + (float)KP * 2.04f * 4.7683716e-7f) * a * rmax + (KP + 5) * u24 * r2 +
                   (KP + 8) * u24 * (a + rmax) * (a + rmax);
         E *= 1.05f;
         const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[129] & 1u) != 0;  // NaN / INF / huge references
@@ -307,22 +329,22 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
 // ---------------------------------------------------------------------------------------------
 struct TensorCand { int q; int unit; float smin; };  // unit = 32 consecutive references (tile * 4 + chunk)
 
-template <int KP>
+template <int KB, int KS, int T_STAGES>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
                      const float* __restrict__ band, unsigned* __restrict__ approx_min,
                      TensorCand* __restrict__ cand, unsigned* __restrict__ cand_count, const unsigned cand_cap)
 {
-    constexpr int KB = KP / 64;                    // 64-element K blocks (one 128-byte swizzle row each)
+    // KB 64-column swizzled blocks (one 128-byte swizzle row each), then KS interleaved 16-column steps
     constexpr uint32_t A_MAIN = KB * T_BM * 128, B_MAIN = KB * T_BN * 128;
-    constexpr uint32_t A_BYTES = (uint32_t)image_bytes(T_BM, KP);  // 72 KiB at KP = 128
-    constexpr uint32_t B_BYTES = (uint32_t)image_bytes(T_BN, KP);  // 36 KiB at KP = 128
+    constexpr uint32_t A_BYTES = (uint32_t)image_bytes(T_BM, KB, KS);  // 72 KiB at KB = 2, KS = 1
+    constexpr uint32_t B_BYTES = (uint32_t)image_bytes(T_BN, KB, KS);  // 36 KiB at KB = 2, KS = 1
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_smem = smem;
     unsigned char* b_smem = smem + A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + T_STAGES * B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_MAX_STAGES + 8);
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_full = bar0, b_empty = bar0 + 8 * T_STAGES;
     const uint32_t acc_full = bar0 + 8 * 2 * T_STAGES, acc_empty = acc_full + 16, a_full = acc_empty + 16;
@@ -378,12 +400,13 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                         }
                     }
                 }
-                {   // extra K step: + |r'|^2
-                    const u64 bdesc = umma_desc_interleave(b_addr + B_MAIN, T_BN);
+#pragma unroll
+                for (int x = 0; x < KS; ++x) {  // interleaved steps (the last columns carry |r'|^2)
+                    const u64 bdesc = umma_desc_interleave(b_addr + B_MAIN + x * (2 * T_BN * 16), T_BN);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const u64 adesc = umma_desc_interleave(a_addr + A_MAIN + h * (128 * 16), T_BM);
-                        tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, 1u);
+                        const u64 adesc = umma_desc_interleave(a_addr + A_MAIN + x * (2 * T_BM * 16) + h * (128 * 16), T_BM);
+                        tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((KB | x) != 0));
                     }
                 }
                 tc_commit(b_empty + 8 * s);      // stage free once these MMAs have read it
@@ -397,7 +420,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         const int half = e >> 2;                // accumulator half (rows 0-127 / 128-255)
         const int row = half * 128 + lq * 32 + lane;
         const long long q = (long long)blockIdx.x * T_BM + row;
-        const float my_band = (q < m) ? band[q] : 0.0f;
+        const float my_band = (q < m) ? band[q] : -inf_f();  // rows past m never qualify
         // other CTAs (reference splits, earlier waves) may already have lowered this query's minimum
         float run_min = (q < m) ? ord2f(approx_min[q]) : inf_f();
         for (int t = 0; t < nt; ++t) {
@@ -405,15 +428,16 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             mbar_wait(acc_full + 8 * buf, (uint32_t)((t >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((buf * 2 + half) * T_BN);
-            uint32_t va[32], vb[32];
+            // all four 32-column loads are issued back to back and waited for once: the epilogue of a
+            // tile costs one TMEM-load latency instead of four
+            uint32_t v[T_BN / 32][32];
             float cmin[T_BN / 32];
-            tmem_ld32(taddr, va);
+#pragma unroll
+            for (int c = 0; c < T_BN / 32; ++c) tmem_ld32(taddr + c * 32, v[c]);
+            tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < T_BN / 32; ++c) {
-                tmem_ld_wait();  // chunk c has landed; fetch chunk c+1 while it is reduced
-                uint32_t (&cur)[32] = (c & 1) ? vb : va;
-                uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-                if (c + 1 < T_BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
+                const uint32_t (&cur)[32] = v[c];
                 // four independent FMNMX3 chains (depth 4) + a 2-level combine instead of one chain of 16
                 float c0 = min3(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]));
                 float c1 = min3(__uint_as_float(cur[8]), __uint_as_float(cur[9]), __uint_as_float(cur[10]));
@@ -435,19 +459,22 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
-            // candidates at 32-reference granularity (one TMEM chunk): 4x less to re-score
+            // candidates at 32-reference granularity (one TMEM chunk): 4x less to re-score than a
+            // tile.  One test per tile on the fast path; the per-unit tests only when it fires.
+            if (fminf(fminf(cmin[0], cmin[1]), fminf(cmin[2], cmin[3])) <= run_min + my_band) {
 #pragma unroll
-            for (int c = 0; c < T_BN / 32; ++c) {
-                if (q < m && cmin[c] <= run_min + my_band) {
-                    const unsigned slot = atomicAdd(cand_count, 1u);
-                    if (slot < cand_cap) {
-                        TensorCand cnd;
-                        cnd.q = (int)q; cnd.unit = (t0 + t) * (T_BN / 32) + c; cnd.smin = cmin[c];
-                        cand[slot] = cnd;
-                    }
-                    if (cmin[c] < run_min) {
-                        run_min = cmin[c];
-                        atomicMin(approx_min + q, f2ord(run_min));
+                for (int c = 0; c < T_BN / 32; ++c) {
+                    if (cmin[c] <= run_min + my_band) {
+                        const unsigned slot = atomicAdd(cand_count, 1u);
+                        if (slot < cand_cap) {
+                            TensorCand cnd;
+                            cnd.q = (int)q; cnd.unit = (t0 + t) * (T_BN / 32) + c; cnd.smin = cmin[c];
+                            cand[slot] = cnd;
+                        }
+                        if (cmin[c] < run_min) {
+                            run_min = cmin[c];
+                            atomicMin(approx_min + q, f2ord(run_min));
+                        }
                     }
                 }
             }
@@ -522,21 +549,22 @@ tensor_rescore_kernel(const float* __restrict__ queries, const int k, const floa
 // ---------------------------------------------------------------------------------------------
 int tensor_kp(int k)
 {
-    const int cols = tensor_split(k) ? 3 * k : k;
-    return cols <= 64 ? 64 : 128;
+    const TensorGeom g = tensor_geom(k);
+    return g.KB * 64 + g.KS * 16;
 }
 
 size_t tensor_section_floats(int k, int n)
 {
     if (k < 1 || k > TENSOR_MAX_K || n <= 0) return 0;
     const size_t nblocks = (size_t)((n + LB - 1) / LB);
-    return (size_t)TENSOR_HDR_FLOATS + nblocks * image_bytes(T_BN, tensor_kp(k)) / 4;
+    const TensorGeom g = tensor_geom(k);
+    return (size_t)TENSOR_HDR_FLOATS + nblocks * image_bytes(T_BN, g.KB, g.KS) / 4;
 }
 
 cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_section, cudaStream_t st)
 {
     if (tensor_section_floats(k, n) == 0) return cudaSuccess;
-    const int KP = tensor_kp(k);
+    const TensorGeom g = tensor_geom(k);
     const int nblocks = (n + LB - 1) / LB;
     float* hdr = d_section;
     unsigned char* image = reinterpret_cast<unsigned char*>(d_section + TENSOR_HDR_FLOATS);
@@ -544,13 +572,27 @@ cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_s
     if (e != cudaSuccess) return e;
     tensor_colsum_kernel<<<(n + 255) / 256, 128, 0, st>>>(d_refs_aos, n, k, hdr);
     tensor_centre_kernel<<<1, 128, 0, st>>>(hdr, n, k);
-    tensor_ref_image_kernel<<<nblocks, 256, 0, st>>>(d_refs_aos, n, k, KP, hdr, image);
+    tensor_ref_image_kernel<<<nblocks, 128, 0, st>>>(d_refs_aos, n, k, g, hdr, image);
     return cudaGetLastError();
 }
 
-size_t tensor_smem_bytes(int KP)
+int tensor_stages(const TensorGeom& g) { return g.KB == 2 ? 4 : g.KB == 1 ? 6 : g.KS == 2 ? 16 : 24; }
+
+size_t tensor_smem_bytes(const TensorGeom& g)
 {
-    return image_bytes(T_BM, KP) + (size_t)T_STAGES * image_bytes(T_BN, KP) + 16 * 8 + 16;
+    return image_bytes(T_BM, g.KB, g.KS) + (size_t)tensor_stages(g) * image_bytes(T_BN, g.KB, g.KS) +
+           (2 * T_MAX_STAGES + 8) * 8 + 16;
+}
+
+template <int KB, int KS, int STAGES>
+static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
+                                        const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
+                                        TensorCand* cand, unsigned* cnt, unsigned cand_cap)
+{
+    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tensor_screen_kernel<KB, KS, STAGES><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cand, cnt, cand_cap);
+    return cudaGetLastError();
 }
 
 // Search m queries against the n references of the index section; accumulates into keys.
@@ -559,7 +601,7 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
                           int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, int* launches,
                           unsigned* d_stats, bool tiny_candidate_buffer)
 {
-    const int KP = tensor_kp(k);
+    const TensorGeom g = tensor_geom(k);
     const int nblocks = (n + LB - 1) / LB;
     const int strips = (m + T_BM - 1) / T_BM;
     const float* hdr = d_section;
@@ -584,7 +626,7 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
 
     // stream-ordered scratch: query image, band, approx_min, candidates, counters.  Every split of
     // a strip emits at least its first tile per query, then running-minimum records + the band.
-    const size_t qimg_bytes = (size_t)strips * image_bytes(T_BM, KP);
+    const size_t qimg_bytes = (size_t)strips * image_bytes(T_BM, g.KB, g.KS);
     const unsigned cand_cap = tiny_candidate_buffer
                                   ? 64u  // test hook: forces the overflow -> wide-kernel fallback
                                   : (unsigned)std::min<size_t>((size_t)m * (64 + 6 * (size_t)splits) + 65536, (size_t)1 << 30);
@@ -604,24 +646,18 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
 
     e = cudaMemsetAsync(cnt, 0, 256, st);
     if (e == cudaSuccess) {
-        tensor_query_image_kernel<<<strips, 256, 0, st>>>(d_queries, m, k, KP, hdr, scratch, band, amin);
+        tensor_query_image_kernel<<<strips, 256, 0, st>>>(d_queries, m, k, g, hdr, scratch, band, amin);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) {
         // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
         // CTA is resident per SM even at KP = 64
-        const size_t smem = std::max(tensor_smem_bytes(KP), (size_t)120 * 1024);
+        const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
         dim3 grid((unsigned)strips, (unsigned)splits);
-        if (KP == 64) {
-            e = cudaFuncSetAttribute(tensor_screen_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess)
-                tensor_screen_kernel<64><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
-        } else {
-            e = cudaFuncSetAttribute(tensor_screen_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess)
-                tensor_screen_kernel<128><<<grid, T_THREADS, smem, st>>>(scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
-        }
-        if (e == cudaSuccess) e = cudaGetLastError();
+        if (g.KB == 0 && g.KS == 1) e = tensor_screen_launch<0, 1, 24>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
+        else if (g.KB == 0) e = tensor_screen_launch<0, 2, 16>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
+        else if (g.KB == 1) e = tensor_screen_launch<1, 1, 6>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
+        else e = tensor_screen_launch<2, 1, 4>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
     }
     if (e == cudaSuccess) {
         const int rgrid = num_sms * 8;
