@@ -330,7 +330,27 @@ def main():
     my_pairs = float(m) * float(r1 - r0)
     kern_pairs_per_s = my_pairs / (kern_ms_avg * 1e-3)
     lane_peak = fp32_peak_tflops * 1e12 / 2.0  # FP32 lane-slots per second
-    if k <= 32 and m >= 16 and not (args.flags & nns_b200.FLAG_FORCE_WIDE):
+    path = nns_b200.plan(k, m, r1 - r0, args.flags)["path"]
+    bf16_peak = float(pk.get("bf16_tflops", 1590.0))
+
+    def exact_form_side_measurement():
+        # the same workload on the exact-form FP32 kernel (outside the headline timing): V0's formulation,
+        # 2k FP32 lane-slots per pair -- the figure the north-star's 70 % FP32 bar refers to
+        xe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for i in range(4):
+            nns_b200._check(nns_b200.lib.nns_b200_keys_init(keys.data_ptr(), m, stream.cuda_stream))
+            if i > 0:
+                xe[i - 1][0].record(stream)
+            index.search_keys(d_q, keys, nns_b200.FLAG_EXACT_FORM, stream)
+            if i > 0:
+                xe[i - 1][1].record(stream)
+        torch.cuda.synchronize()
+        x_ms = sum(a.elapsed_time(b) for a, b in xe) / len(xe)
+        x_rate = my_pairs / (x_ms * 1e-3)
+        return {"kernel_ms": x_ms, "kernel_pairs_per_s": x_rate, "executed_lane_slots_per_pair": 2 * k,
+                "frac": x_rate * 2.0 * k / lane_peak}
+
+    if path == 0:
         # Executed FP32 lane-slots per pair: the screened kernel evaluates
         # s = |r|^2 - 2q.r with k FMAs per pair; the exact-form kernel runs V0's k subtractions +
         # k FMAs (2k; 3k with separately rounded mul/add).  `frac` is computed from the slots the
@@ -351,31 +371,43 @@ def main():
                     "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s}
         if clocks.get("sm_mhz"):
             roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
-        if not (args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING)):
-            # the same workload on the exact-form kernel (outside the headline timing), so that
-            # both formulations' FP32-pipe fractions are measured in one run
-            xe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
-            for i in range(4):
-                nns_b200._check(nns_b200.lib.nns_b200_keys_init(keys.data_ptr(), m, stream.cuda_stream))
-                if i > 0:
-                    xe[i - 1][0].record(stream)
-                index.search_keys(d_q, keys, args.flags | nns_b200.FLAG_EXACT_FORM, stream)
-                if i > 0:
-                    xe[i - 1][1].record(stream)
-            torch.cuda.synchronize()
-            x_ms = sum(a.elapsed_time(b) for a, b in xe) / len(xe)
-            x_rate = my_pairs / (x_ms * 1e-3)
-            roofline["exact_form_kernel"] = {"kernel_ms": x_ms, "kernel_pairs_per_s": x_rate, "executed_lane_slots_per_pair": 2 * k,
-                                             "frac": x_rate * 2.0 * k / lane_peak}
-    elif nns_b200.plan(k, m, r1 - r0, args.flags)["path"] == 2:
+        if not (args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING)) and m >= 16:
+            roofline["exact_form_kernel"] = exact_form_side_measurement()
+    elif path == 2 and k <= 32:
+        # Split-precision tcgen05 screen for low k: the contraction is 16-64 BF16 columns,
+        # so the tensor pipe idles and what every pair still costs is ONE minimum on the 128-lane/clk/SM
+        # ALU pipe (FMNMX3 retires two new values per instruction at half rate) in the epilogue that
+        # reduces the TMEM accumulators.  SURVEY.md 8(d): a kernel that executes fewer than V0's 2k
+        # lane-slots per pair is priced at the slots it executes -> 1 per pair, against the same
+        # 128 lanes x 148 SMs x f peak as the FP32 kernels.  The tensor-pipe fractions are reported
+        # beside it: `tensor_frac` counts the algorithmic 2k FLOPs per pair, `tensor_frac_executed`
+        # the 2 x padded-contraction FLOPs the MMAs really perform.
+        kp = nns_b200.tensor_kp(k)
+        achieved = kern_pairs_per_s * 1 * 2.0 / 1e12
+        roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                    "frac": achieved / fp32_peak_tflops, "traffic": None,
+                    "kernel": "tcgen05 split-precision BF16 screen (K = %d columns) + query image + exact FP32 re-score; "
+                              "bound by one FMNMX3 lane-slot per pair in the TMEM epilogue" % kp,
+                    "executed_lane_slots_per_pair": 1,
+                    "v0_form_frac": kern_pairs_per_s * 2.0 * k / lane_peak,
+                    "tensor_frac": kern_pairs_per_s * 2.0 * k / 1e12 / bf16_peak,
+                    "tensor_frac_executed": kern_pairs_per_s * 2.0 * kp / 1e12 / bf16_peak,
+                    "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz ({pk_src} sm_max_mhz; the ALU-pipe lane rate "
+                                   f"equals the FP32 lane rate; bf16_tflops {pk_src})",
+                    "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": nns_b200.tensor_stats()}
+        if clocks.get("sm_mhz"):
+            roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
+        roofline["exact_form_kernel"] = exact_form_side_measurement()
+    elif path == 2:
         # tcgen05 path: 2k FLOPs per pair (the -2 q.r contraction only; norms, epilogue and the exact
         # re-score count as zero) against the measured dense BF16 peak
         achieved = kern_pairs_per_s * 2.0 * k / 1e12
-        peak = float(pk.get("bf16_tflops", 1590.0))
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
                     "traffic": None, "peak_source": f"{pk_src} bf16_tflops (burst, cuBLAS 8192^3)",
-                    "kernel": "tcgen05 BF16 screen (K padded to %d) + query image + exact FP32 re-score" % (64 if k <= 64 else 128),
+                    "kernel": "tcgen05 BF16 screen (K = %d columns) + query image + exact FP32 re-score" % nns_b200.tensor_kp(k),
                     "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": nns_b200.tensor_stats()}
+        if clocks.get("sm_mhz"):
+            roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
     else:
         # reference-parallel kernel (k > 128, or very few queries)
         hbm = float(pk.get("hbm_gbs", 6650.0))
@@ -392,7 +424,7 @@ def main():
                         "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz"}
 
     if world == 1:
-        pname = {0: "lowk", 1: "wide", 2: "tensor"}[nns_b200.plan(k, m, r1 - r0, args.flags)["path"]]
+        pname = {0: "lowk", 1: "wide", 2: "tensor"}[path]
         if args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING):
             pname += "_exact"
         roofline["traffic"] = ncu_traffic(name, pname)

@@ -74,9 +74,15 @@ struct Plan {
     int smem;    // dynamic shared memory bytes
 };
 
-// k <= 32, m >= 256: run the split-precision tcgen05 screen instead of the FP32 screened kernel
-// (set from the B200 measurements in profiles/; both return identical indices)
-static const bool LOWK_AUTO_TENSOR = false;
+// k <= 32: the split-precision tcgen05 screen (csrc/tensor_search.cu) beats the FP32 screened kernel
+// once the problem amortises its fixed cost (query image, four launches, per-CTA TMEM set-up):
+// B200, profiles/r1_tensor_*: C2 (k = 3, 2.7e11 pairs) 18.6 ms vs 39.9 ms, C3 (k = 16) 0.49 s vs 2.6 s,
+// C1 (6.7e7 pairs) 0.38 ms vs 0.064 ms.  Both paths return identical indices.
+static bool lowk_prefers_tensor(int k, int m, int n)
+{
+    const double pairs = (double)m * (double)n;
+    return m >= 1024 && pairs >= (k <= 8 ? 4e9 : 1e9);
+}
 
 typedef int (*occ_fn)(void* user, int k, int q, int mode, int warps, int stages);
 
@@ -141,7 +147,7 @@ static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn oc
     const bool tensor_ok = k <= TENSOR_MAX_K;
     if ((flags & NNS_B200_FLAG_FORCE_TENSOR) && !tensor_ok)
         return fail(NNS_B200_ERR_UNSUPPORTED, "tensor path needs k <= %d", TENSOR_MAX_K);
-    const bool tensor_auto = m >= 256 && (k > LOWK_MAX_K || (LOWK_AUTO_TENSOR && !(flags & NNS_B200_FLAG_EXACT_FORM)));
+    const bool tensor_auto = k > LOWK_MAX_K ? m >= 256 : (lowk_prefers_tensor(k, m, n) && !(flags & NNS_B200_FLAG_EXACT_FORM));
     if (tensor_ok && !(flags & (NNS_B200_FLAG_FORCE_WIDE | NNS_B200_FLAG_FORCE_LOWK)) &&
         ((flags & NNS_B200_FLAG_FORCE_TENSOR) || tensor_auto)) {
         // tcgen05 path: one CTA per 256-query strip x reference range (splits chosen at launch)
@@ -341,7 +347,29 @@ static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_quer
         CU_TRY(tensor_search(k, m, n, d_queries, d_blocks, d_section, index_base, d_keys, mode == LOWK_EXACT_V0,
                              c->num_sms, st, &launches, (unsigned*)c->stats.p,
                              (flags & NNS_B200_FLAG_TEST_TINY_CANDIDATES) != 0));
-        g_launches.fetch_add((unsigned long long)launches, std::memory_order_relaxed);
+        g_launches.fetch_add((unsigned long long)launches + 1, std::memory_order_relaxed);
+        // Fallback for data whose near-ties overflow the candidate buffer (e.g. all points identical, or
+        // clusters far denser than the BF16 screen resolves): the FP32 kernel of this shape, launched
+        // unconditionally behind the device-side flag the re-score kernel leaves in stats[1]; it
+        // exits at once when the flag is clear.  No host round trip.
+        const int* enable = (const int*)c->stats.p + 1;
+        unsigned fb = (flags & ~(NNS_B200_FLAG_FORCE_TENSOR | NNS_B200_FLAG_TEST_TINY_CANDIDATES)) |
+                      ((k <= LOWK_MAX_K && m >= 16) ? NNS_B200_FLAG_FORCE_LOWK : NNS_B200_FLAG_FORCE_WIDE);
+        ST_TRY(make_plan(k, m, n, fb, c->num_sms, occ_query, c, &p));
+        if (p.path == 0) {
+            LowkArgs a{};
+            a.queries = d_queries; a.m = m; a.header = d_header; a.blocks = d_blocks; a.nblocks = nblocks;
+            a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
+            a.warps = p.warps; a.stages = p.stages; a.nqb = p.nqb; a.splits = p.splits; a.stream = st;
+            a.enable = enable;
+            CU_TRY(lowk_dispatch(k, p.q, mode, a, nullptr));
+        } else {
+            WideArgs a{};
+            a.queries = d_queries; a.m = m; a.k = k; a.blocks = d_blocks; a.nblocks = nblocks;
+            a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
+            a.nqg = p.nqb; a.splits = p.splits; a.stream = st; a.enable = enable;
+            CU_TRY(wide_launch(mode == LOWK_EXACT_V0, a));
+        }
         return NNS_B200_OK;
     }
     if (p.path == 0) {
@@ -413,8 +441,13 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
     // chunk = about 32 MiB of AoS reference data, a whole number of reference blocks
     long long chunk = ((32ll << 20) / ((long long)k * 4)) / LB * LB;
     if (chunk < LB) chunk = LB;
-    const bool has_tensor = tensor_section_floats(k, n) != 0;
-    if (has_tensor) chunk = ((long long)n + LB - 1) / LB * LB;  // the centre needs the whole reference set
+    // The tensor section (centre, BF16 operand image) is only built when this call is planned onto the
+    // tcgen05 path; the planner's choice is monotone in n, so the chunks of a search that is not
+    // never pick it either.  The centre needs the whole reference set: one chunk.
+    Plan whole{};
+    if (n > 0) ST_TRY(make_plan(k, m, n, host_flags(), c->num_sms, nullptr, nullptr, &whole));
+    const bool has_tensor = whole.path == 2 && tensor_section_floats(k, n) != 0;
+    if (has_tensor) chunk = ((long long)n + LB - 1) / LB * LB;
     const int nchunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
     while ((int)c->events.size() < nchunks) {
         cudaEvent_t ev;

@@ -55,6 +55,7 @@ struct LowkArgs {
     int nqb;               // query blocks (grid.x)
     int splits;            // reference splits (grid.y)
     cudaStream_t stream;
+    const int* enable = nullptr;  // optional device flag: the kernel exits immediately when it is 0
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -172,10 +173,11 @@ template <int K, int Q, bool EXACT, int MINB, int UNROLL>
 __global__ void __launch_bounds__(288, MINB)
 lowk_exact_kernel(const float* __restrict__ queries, const int m, const float* __restrict__ blocks,
                   const int nblocks, const int blocks_per_split, const int index_base, const int stages,
-                  u64* __restrict__ keys)
+                  u64* __restrict__ keys, const int* __restrict__ enable)
 {
     using Ring = TileRing<K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (enable && *enable == 0) return;        // fallback launch that turned out not to be needed
     const int W = (int)(blockDim.x >> 5) - 1;  // consumer warps; warp W is the producer
     const int warp = (int)(threadIdx.x >> 5);
     const int lane = (int)(threadIdx.x & 31);
@@ -302,10 +304,11 @@ template <int K, int Q, int MINB, int UNROLL, int G>
 __global__ void __launch_bounds__(288, MINB)
 lowk_filter_kernel(const float* __restrict__ queries, const int m, const float* __restrict__ header,
                    const float* __restrict__ blocks, const int nblocks, const int blocks_per_split,
-                   const int index_base, const int stages, u64* __restrict__ keys)
+                   const int index_base, const int stages, u64* __restrict__ keys, const int* __restrict__ enable)
 {
     using Ring = TileRing<K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (enable && *enable == 0) return;  // fallback launch that turned out not to be needed
     const int W = (int)(blockDim.x >> 5) - 1;
     const int warp = (int)(threadIdx.x >> 5);
     const int lane = (int)(threadIdx.x & 31);
@@ -442,9 +445,9 @@ cudaError_t lowk_launch_kernel(Kern kern, int K, const LowkArgs& a, int* occupan
     if (occupancy_out) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy_out, kern, threads, smem);
     dim3 grid((unsigned)a.nqb, (unsigned)a.splits);
     void* args_h[] = {(void*)&a.queries, (void*)&a.m, (void*)&a.header, (void*)&a.blocks, (void*)&a.nblocks,
-                      (void*)&a.blocks_per_split, (void*)&a.index_base, (void*)&a.stages, (void*)&a.keys};
+                      (void*)&a.blocks_per_split, (void*)&a.index_base, (void*)&a.stages, (void*)&a.keys, (void*)&a.enable};
     void* args_n[] = {(void*)&a.queries, (void*)&a.m, (void*)&a.blocks, (void*)&a.nblocks,
-                      (void*)&a.blocks_per_split, (void*)&a.index_base, (void*)&a.stages, (void*)&a.keys};
+                      (void*)&a.blocks_per_split, (void*)&a.index_base, (void*)&a.stages, (void*)&a.keys, (void*)&a.enable};
     return cudaLaunchKernel((const void*)kern, grid, dim3(threads), with_header ? args_h : args_n, smem, a.stream);
 }
 

@@ -1,34 +1,44 @@
-// tensor_search.cu -- the k > 32 path (BASELINE config C4, k = 128): the dense contraction
-// -2 Q.R^T runs on the 5th-generation tensor cores (tcgen05.mma, BF16 operands, FP32 accumulators
-// in TMEM), a fused epilogue reduces every 128-reference tile to a per-query minimum of the
-// approximate score S~ = |r'|^2 - 2 q'.r' and emits (query, tile) candidates, and an exact FP32
-// re-score of the candidate tiles in V0's subtract-square-accumulate form (core.cu:38-43) decides
-// the answer.  The m x n score matrix never leaves TMEM.
+// tensor_search.cu -- the tcgen05 path.  Built for k > 32 (BASELINE config C4, k = 128): the dense
+// contraction -2 Q.R^T runs on the 5th-generation tensor cores (tcgen05.mma, BF16 operands, FP32
+// accumulators in TMEM), a fused epilogue reduces every 128-reference tile to per-query minima of the
+// approximate score S~ = |r'|^2 - 2 q'.r' and emits (query, 32-reference unit) candidates, and an exact
+// FP32 re-score of the candidates in V0's subtract-square-accumulate form (core.cu:38-43) decides the
+// answer.  The m x n score matrix never leaves TMEM.  With split-precision BF16 columns the same
+// screen also serves k <= 32 on large problems (C2, C3), where it is bound by one FMNMX3 lane-slot
+// per pair instead of the k FFMA2 lane-slots of the FP32 screened kernel.
 //
 // Exactness.  q' = fl(q - c), r' = fl(r - c) are the inputs centred on the reference mean c
 // (distances are translation invariant; centring shrinks the operands ~4x for data in [0,1]).
-// The tensor cores see bf16(-2q') and bf16(r'); E(q) bounds |S~ - S| for every reference plus the
-// gap between V0's FP32 distance and the real one (tensor_band_kernel).  A tile is a candidate
-// when its minimum S~ is within 2E of the running minimum, and is re-scored when it is within 2E
-// of the final minimum: the tile holding V0's answer always qualifies, as does every tile holding
-// an exactly tied reference, and the re-score keeps the lowest index through the packed-key
-// atomicMin.  If the candidate buffer overflows (adversarial data: e.g. all points identical) a
-// device flag makes the FP32 wide kernel redo the search -- there is no host round trip.
+// The tensor cores see bf16(-2q') and bf16(r') (hi + lo parts for k <= 42); E(q) bounds |S~ - S| for
+// every reference plus the gap between V0's FP32 distance and the real one
+// (tensor_query_image_kernel).  A unit is a candidate when its minimum S~ is within 2E of the running
+// minimum, and is re-scored when it is within 2E of the final minimum: the unit holding V0's answer
+// always qualifies, as does every unit holding an exactly tied reference, and the re-score keeps the
+// lowest index through the packed-key atomicMin.  If the candidate buffer overflows (adversarial data:
+// all points identical, clusters far denser than the screen resolves) a device flag makes the FP32
+// kernel launched right behind redo the search -- there is no host round trip -- and screen CTAs that
+// have not started yet give up at once.
 //
-// Kernel structure (one CTA per 256-query strip x reference range, 10 warps):
+// Kernel structure (one CTA per 256-query strip x reference range, 18 warps, one CTA per SM):
 //   warp 0   producer: 1-D bulk copies (TMA) of the pre-swizzled BF16 images: the strip's A tile
-//            once (64 KiB), then the B tiles (32 KiB per 128 references) through a 4-stage ring
+//            once, then the B tiles through an mbarrier ring (G tiles per stage: 4 KiB tiles are
+//            moved four at a time so that the ring costs one barrier round trip per 16 KiB)
 //   warp 1   MMA issuer: one elected lane issues tcgen05.mma.kind::f16 M=128 N=128 K=16, two
-//            accumulator halves (query rows 0-127 / 128-255) x double-buffered = all 512 TMEM columns;
-//            tcgen05.commit releases the B stage and publishes the accumulator
-//   warps 2-9 epilogue: one thread per query row; tcgen05.ld 32 columns at a time (double
-//            buffered), FMNMX3 running minimum, candidate test.  |r'|^2 is folded into the
-//            contraction as one extra K = 16 step (A carries 1,1,1; B carries |r'|^2 split into three
-//            BF16 terms), so the epilogue touches neither shared memory nor the FP32 pipe: shared
-//            memory bandwidth is what the MMA operand fetch needs (M = N = 128: 128 B/clk).
-// Operand images are K-major with the 128-byte swizzle (Swizzle<3,4,3>), written by the prep
-// kernels exactly as the UMMA shared-memory descriptors expect them, so plain bulk copies suffice
-// (no tensor maps).  SASS: UTCHMMA / LDTM / UBLKCP.
+//            accumulator halves (query rows 0-127 / 128-255) x two buffers = all 512 TMEM columns;
+//            tcgen05.commit publishes the accumulator and releases the B stage
+//   warps 2-17 epilogue, two teams of 8 warps: team i owns TMEM buffer i and reduces the tiles
+//            t % 2 == i; thread = query row; tcgen05.ld 32 columns at a time, FMNMX3 tree, candidate
+//            test.  |r'|^2 is folded into the contraction (A carries 1,1,1; B carries |r'|^2 split
+//            into three BF16 terms), so the epilogue touches neither shared memory nor the FP32 pipe.
+// Why two teams: for short contractions the tile pipeline is a chain of latencies -- commit ->
+// epilogue wake-up -> four TMEM-load round trips -> release -> issuer wake-up -> MMA issue -> MMA --
+// of ~1300 clk per TMEM buffer, of which only ~150 clk per warp are FMNMX3 issue slots
+// (tools/tensor_trace.py, profiles/r1_tensor_trace_*.txt).  Two teams keep both buffers' chains
+// running concurrently with four epilogue warps per scheduler.
+// Operand images are K-major with the 128-byte swizzle (Swizzle<3,4,3>), or K-major "interleaved"
+// 8 x 16 B core matrices for the 16-column steps, written by the prep kernels exactly as the UMMA
+// shared-memory descriptors expect them, so plain bulk copies suffice (no tensor maps).
+// SASS: UTCHMMA / LDTM / UBLKCP.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -39,9 +49,32 @@ namespace nns {
 
 constexpr int T_BM = 256;     // query rows per CTA (two M = 128 accumulator halves)
 constexpr int T_BN = 128;     // references per tile == one index block
-constexpr int T_MAX_STAGES = 24;  // B ring depth is chosen per geometry: small tiles need a deep ring to cover the TMA latency
-constexpr int T_THREADS = 320;
-constexpr int T_EPI_WARPS = 8;
+constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarrier area is sized for it)
+// experiment knobs (tools/tensor_tune.sh builds the variants; the defaults are the measured best)
+#ifndef NNS_T_TEAMS
+#define NNS_T_TEAMS 2       // epilogue teams of 8 warps; team i owns TMEM buffer i and reduces the tiles t % 2 == i
+#endif
+#ifndef NNS_T_SPIN
+#define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
+#endif
+#ifndef NNS_T_EXPERIMENT
+#define NNS_T_EXPERIMENT 0  // timing experiments only (wrong results): 1 = epilogue reduces 2 of 32 columns,
+#endif                      // 2 = epilogue does not read TMEM at all, 3 = additionally no MMA is issued
+#ifdef NNS_T_TRACE  // = first tile of the 32-tile window: clock64() timeline of CTA (0,0), tools/tensor_trace.py
+__device__ long long g_ttrace[36][32];
+#define T_TRACE(ev, t) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (t) >= NNS_T_TRACE && (t) < NNS_T_TRACE + 32) g_ttrace[ev][(t) - NNS_T_TRACE] = clock64(); } while (0)
+extern "C" int nns_b200_debug_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_ttrace, sizeof(g_ttrace)); }
+#else
+#define T_TRACE(ev, t) ((void)0)
+#endif
+constexpr int T_TEAMS = NNS_T_TEAMS;
+constexpr int T_TEAM_WARPS = 8;                        // one warp per (TMEM lane quarter, accumulator half)
+constexpr int T_SERVICE_WARPS = 2;                     // warp 0 = TMA producer, warp 1 = MMA issuer
+constexpr int T_THREADS = 32 * (T_SERVICE_WARPS + T_TEAMS * T_TEAM_WARPS);
+// one CTA per SM: the whole register file.  Registers are per scheduler (16384 each), and the
+// busiest one hosts ceil(warps / 4) warps
+constexpr int T_MAX_REGS = (16384 / (32 * ((T_THREADS / 32 + 3) / 4))) & ~7;
+constexpr int T_CPW = T_BN / 32;                       // 32-column chunks per epilogue warp per tile
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM helpers
@@ -122,6 +155,30 @@ __device__ __forceinline__ float ord2f(unsigned o)
     return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
+// mbarrier waits on the MMA <-> epilogue critical path.  NNS_T_SPIN bit 0: the epilogue warps poll
+// (try_wait without a suspend hint) instead of sleeping on the barrier; bit 1: the MMA issuer polls.
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity)  // epilogue
+{
+    if (NNS_T_SPIN & 1) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait_mma(uint32_t bar, uint32_t parity)  // MMA issuer
+{
+    if (NNS_T_SPIN & 2) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity);
+}
+
 // byte offset of element (row, t) inside an operand image with `rows` rows:
 // [t/64][rows][128 B], 16-byte chunks XOR-swizzled with the row (Swizzle<3,4,3>)
 __device__ __forceinline__ size_t image_chunk_offset(int rows, int row, int kb, int chunk)
@@ -142,9 +199,12 @@ __host__ __device__ inline TensorGeom tensor_geom(int k)
     TensorGeom g;
     g.split = k <= TENSOR_SPLIT_MAX_K ? 1 : 0;
     g.ndata = g.split ? 3 * k : k;
+    // the three norm columns ride in the last block whenever it has room for them
     if (g.ndata + 3 <= 16) { g.KB = 0; g.KS = 1; g.norm_col = g.ndata; }
     else if (g.ndata + 3 <= 32) { g.KB = 0; g.KS = 2; g.norm_col = g.ndata; }
+    else if (g.ndata + 3 <= 64) { g.KB = 1; g.KS = 0; g.norm_col = g.ndata; }
     else if (g.ndata <= 64) { g.KB = 1; g.KS = 1; g.norm_col = 64; }
+    else if (g.ndata + 3 <= 128) { g.KB = 2; g.KS = 0; g.norm_col = g.ndata; }
     else { g.KB = 2; g.KS = 1; g.norm_col = 128; }
     return g;
 }
@@ -329,22 +389,52 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
 // ---------------------------------------------------------------------------------------------
 struct TensorCand { int q; int unit; float smin; };  // unit = 32 consecutive references (tile * 4 + chunk)
 
-template <int KB, int KS, int T_STAGES>
-__global__ void __launch_bounds__(T_THREADS, 1)
+// Candidate buffer.  Every CTA of the screen owns a private region of `region_cap` records and
+// allocates slots from a SHARED-memory counter, so that emitting a candidate never waits for a
+// global atomic round trip (~600 clk, measured with tools/tensor_trace.py: the epilogue warp that
+// waited stalled the MMA issuer through the accumulator hand-off).  A CTA whose region is full
+// spills into a common region through a global counter; only if that overflows too does the FP32
+// wide kernel redo the search.
+struct CandBuf {
+    TensorCand* rec;       // [n_ctas * region_cap] CTA regions, then [common_cap] common records
+    unsigned* cta_count;   // [n_ctas] records used in each CTA region
+    unsigned* counters;    // [0] common records requested, [1] overflow flag, [2] total records emitted
+    unsigned region_cap;   // multiple of 32
+    unsigned common_cap;
+    unsigned n_ctas;
+};
+
+__device__ __forceinline__ void cand_emit(const CandBuf& cb, unsigned* s_count, const unsigned cta, const TensorCand& c)
+{
+    const unsigned slot = atomicAdd(s_count, 1u);  // shared memory; warp-aggregated by the compiler
+    if (slot < cb.region_cap) {
+        cb.rec[(size_t)cta * cb.region_cap + slot] = c;
+    } else {
+        const unsigned g = atomicAdd(cb.counters, 1u);
+        if (g < cb.common_cap) cb.rec[(size_t)cb.n_ctas * cb.region_cap + g] = c;
+        else cb.counters[1] = 1u;  // out of space: CTAs that have not started yet give up at once
+    }
+}
+
+// G = reference tiles per TMA stage: short contractions (KB = 0) move 4 KiB / 8 KiB tiles, and one
+// mbarrier round trip per tile on the MMA issuer's critical path costs more than the MMAs themselves
+template <int KB, int KS, int T_STAGES, int G>
+__global__ void __maxnreg__(T_MAX_REGS)
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
-                     const float* __restrict__ band, unsigned* __restrict__ approx_min,
-                     TensorCand* __restrict__ cand, unsigned* __restrict__ cand_count, const unsigned cand_cap)
+                     const float* __restrict__ band, unsigned* __restrict__ approx_min, const CandBuf cb)
 {
     // KB 64-column swizzled blocks (one 128-byte swizzle row each), then KS interleaved 16-column steps
     constexpr uint32_t A_MAIN = KB * T_BM * 128, B_MAIN = KB * T_BN * 128;
     constexpr uint32_t A_BYTES = (uint32_t)image_bytes(T_BM, KB, KS);  // 72 KiB at KB = 2, KS = 1
     constexpr uint32_t B_BYTES = (uint32_t)image_bytes(T_BN, KB, KS);  // 36 KiB at KB = 2, KS = 1
+    constexpr uint32_t STAGE_BYTES = G * B_BYTES;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_smem = smem;
     unsigned char* b_smem = smem + A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + T_STAGES * B_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + T_STAGES * STAGE_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_MAX_STAGES + 8);
+    unsigned* s_cand_count = tmem_slot + 1;
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_full = bar0, b_empty = bar0 + 8 * T_STAGES;
     const uint32_t acc_full = bar0 + 8 * 2 * T_STAGES, acc_empty = acc_full + 16, a_full = acc_empty + 16;
@@ -352,13 +442,20 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     const int t0 = (int)blockIdx.y * tiles_per_split;
     const int nt = min(ntiles, t0 + tiles_per_split) - t0;
-    if (nt <= 0) return;
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    // nothing to do, or an earlier CTA ran out of candidate space (dense near-ties: the FP32 kernel
+    // launched after the re-score redoes the whole search, so the rest of this pass would be wasted)
+    if (nt <= 0 || *reinterpret_cast<volatile const unsigned*>(cb.counters + 1) != 0u) {
+        if (threadIdx.x == 0) cb.cta_count[cta] = 0;
+        return;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_TEAM_WARPS); }
         mbar_init(a_full, 1);
         mbar_fence_init();
+        *s_cand_count = 0;
     }
     if (warp == 1) tmem_alloc512(smem_u32(tmem_slot));
     tc_fence_before();
@@ -371,23 +468,30 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         if (lane == 0) {
             mbar_arrive_expect_tx(a_full, A_BYTES);
             bulk_g2s(smem_u32(a_smem), qimage + (size_t)blockIdx.x * A_BYTES, A_BYTES, a_full);
-            for (int t = 0; t < nt; ++t) {
-                const int s = t % T_STAGES;
-                mbar_wait(b_empty + 8 * s, (uint32_t)(((t / T_STAGES) & 1) ^ 1));
-                mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES);
-                bulk_g2s(smem_u32(b_smem + (size_t)s * B_BYTES), rimage + (size_t)(t0 + t) * B_BYTES, B_BYTES, b_full + 8 * s);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int g0 = 0; g0 < nt; g0 += G) {
+                mbar_wait(b_empty + 8 * s, ph ^ 1u);
+                T_TRACE(0, g0);
+                const uint32_t bytes = (uint32_t)min(G, nt - g0) * B_BYTES;
+                mbar_arrive_expect_tx(b_full + 8 * s, bytes);
+                bulk_g2s(smem_u32(b_smem + (size_t)s * STAGE_BYTES), rimage + (size_t)(t0 + g0) * B_BYTES, bytes, b_full + 8 * s);
+                if (++s == T_STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             mbar_wait(a_full, 0);
+            int s = 0, j = 0;
+            uint32_t ph = 0;
+            const uint32_t a_addr = smem_u32(a_smem);
             for (int t = 0; t < nt; ++t) {
-                const int s = t % T_STAGES, buf = t & 1;
-                mbar_wait(acc_empty + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));  // epilogue drained this buffer
-                mbar_wait(b_full + 8 * s, (uint32_t)((t / T_STAGES) & 1));       // TMA landed this stage
+                const int buf = t & 1;
+                mbar_wait_mma(acc_empty + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));  // its team drained this buffer
+                if (j == 0) mbar_wait_mma(b_full + 8 * s, ph);                      // TMA landed this stage
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(a_smem), b_addr = smem_u32(b_smem + (size_t)s * B_BYTES);
+                const uint32_t b_addr = smem_u32(b_smem + (size_t)s * STAGE_BYTES + (size_t)j * B_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
@@ -396,7 +500,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const u64 adesc = umma_desc_sw128(a_addr + kb * (T_BM * 128) + h * (128 * 128) + ks * 32);
-                            tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((kb | ks) != 0));
+                            if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((kb | ks) != 0));
                         }
                     }
                 }
@@ -406,111 +510,157 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const u64 adesc = umma_desc_interleave(a_addr + A_MAIN + x * (2 * T_BM * 16) + h * (128 * 16), T_BM);
-                        tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((KB | x) != 0));
+                        if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((KB | x) != 0));
                     }
                 }
-                tc_commit(b_empty + 8 * s);      // stage free once these MMAs have read it
                 tc_commit(acc_full + 8 * buf);   // accumulator complete
+                T_TRACE(3, t);
+                if (j == G - 1 || t == nt - 1) {
+                    tc_commit(b_empty + 8 * s);  // stage free once the MMAs of its tiles have read it
+                    j = 0;
+                    if (++s == T_STAGES) { s = 0; ph ^= 1u; }
+                } else {
+                    ++j;
+                }
             }
         }
     } else {
         // ---------------- epilogue: thread = query row ----------------
-        const int e = warp - 2;                 // 0..7
+        // Two teams of 8 warps.  Team i owns TMEM buffer i and reduces the tiles t % 2 == i, so a
+        // team has TWO tile periods for the serial path of one tile (wait, four TMEM-load round
+        // trips, 76 FMNMX3, release -- ~700 clk measured with tools/tensor_trace.py, of which only
+        // 150 clk are issue slots); with 4 epilogue warps per scheduler the ALU pipe stays busy.
+        const int e = warp - T_SERVICE_WARPS;
+        const int team = e >> 3;                // TMEM buffer / tile parity (0 when T_TEAMS == 1)
         const int lq = warp & 3;                // TMEM lane quarter this warp may access
-        const int half = e >> 2;                // accumulator half (rows 0-127 / 128-255)
+        const int half = (e >> 2) & 1;          // accumulator half (rows 0-127 / 128-255)
         const int row = half * 128 + lq * 32 + lane;
         const long long q = (long long)blockIdx.x * T_BM + row;
         const float my_band = (q < m) ? band[q] : -inf_f();  // rows past m never qualify
         // other CTAs (reference splits, earlier waves) may already have lowered this query's minimum
         float run_min = (q < m) ? ord2f(approx_min[q]) : inf_f();
-        for (int t = 0; t < nt; ++t) {
-            const int buf = t & 1;
-            mbar_wait(acc_full + 8 * buf, (uint32_t)((t >> 1) & 1));
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((buf * 2 + half) * T_BN);
-            // all four 32-column loads are issued back to back and waited for once: the epilogue of a
-            // tile costs one TMEM-load latency instead of four
-            uint32_t v[T_BN / 32][32];
-            float cmin[T_BN / 32];
+        float thresh = run_min + my_band;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * T_BN);
+        // One TMEM chunk in flight per warp: with four epilogue warps per scheduler the load latency
+        // of one warp is covered by the reductions of the other three.  (A register double buffer
+        // measured no faster at k = 3 and slower at k = 128, where the box runs at its power cap.)
+        uint32_t v[1][32];
+#if NNS_T_EXPERIMENT >= 2
 #pragma unroll
-            for (int c = 0; c < T_BN / 32; ++c) tmem_ld32(taddr + c * 32, v[c]);
-            tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) v[0][i] = 0x7f800000u;
+#define tmem_ld32(a, b) ((void)0)
+#endif
+        // reduce one 32-column chunk, emit it as a candidate when it is within the band
+        auto reduce_chunk = [&](const uint32_t (&cur)[32], const int t, const int c) {
+#if NNS_T_EXPERIMENT >= 1
+            const float cm = fminf(__uint_as_float(cur[0]), __uint_as_float(cur[31]));
+#else
+            // four independent FMNMX3 chains (depth 4) + a 2-level combine
+            float c0 = min3(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]));
+            float c1 = min3(__uint_as_float(cur[8]), __uint_as_float(cur[9]), __uint_as_float(cur[10]));
+            float c2 = min3(__uint_as_float(cur[16]), __uint_as_float(cur[17]), __uint_as_float(cur[18]));
+            float c3 = min3(__uint_as_float(cur[24]), __uint_as_float(cur[25]), __uint_as_float(cur[26]));
 #pragma unroll
-            for (int c = 0; c < T_BN / 32; ++c) {
-                const uint32_t (&cur)[32] = v[c];
-                // four independent FMNMX3 chains (depth 4) + a 2-level combine instead of one chain of 16
-                float c0 = min3(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]));
-                float c1 = min3(__uint_as_float(cur[8]), __uint_as_float(cur[9]), __uint_as_float(cur[10]));
-                float c2 = min3(__uint_as_float(cur[16]), __uint_as_float(cur[17]), __uint_as_float(cur[18]));
-                float c3 = min3(__uint_as_float(cur[24]), __uint_as_float(cur[25]), __uint_as_float(cur[26]));
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    c0 = min3(c0, __uint_as_float(cur[3 + 2 * j]), __uint_as_float(cur[4 + 2 * j]));
-                    c1 = min3(c1, __uint_as_float(cur[11 + 2 * j]), __uint_as_float(cur[12 + 2 * j]));
-                    c2 = min3(c2, __uint_as_float(cur[19 + 2 * j]), __uint_as_float(cur[20 + 2 * j]));
-                    c3 = min3(c3, __uint_as_float(cur[27 + 2 * j]), __uint_as_float(cur[28 + 2 * j]));
-                }
-                c0 = fminf(c0, __uint_as_float(cur[7]));
-                c1 = fminf(c1, __uint_as_float(cur[15]));
-                c2 = fminf(c2, __uint_as_float(cur[23]));
-                c3 = fminf(c3, __uint_as_float(cur[31]));
-                cmin[c] = fminf(min3(c0, c1, c2), c3);
+            for (int j = 0; j < 2; ++j) {
+                c0 = min3(c0, __uint_as_float(cur[3 + 2 * j]), __uint_as_float(cur[4 + 2 * j]));
+                c1 = min3(c1, __uint_as_float(cur[11 + 2 * j]), __uint_as_float(cur[12 + 2 * j]));
+                c2 = min3(c2, __uint_as_float(cur[19 + 2 * j]), __uint_as_float(cur[20 + 2 * j]));
+                c3 = min3(c3, __uint_as_float(cur[27 + 2 * j]), __uint_as_float(cur[28 + 2 * j]));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
-            // candidates at 32-reference granularity (one TMEM chunk): 4x less to re-score than a
-            // tile.  One test per tile on the fast path; the per-unit tests only when it fires.
-            if (fminf(fminf(cmin[0], cmin[1]), fminf(cmin[2], cmin[3])) <= run_min + my_band) {
-#pragma unroll
-                for (int c = 0; c < T_BN / 32; ++c) {
-                    if (cmin[c] <= run_min + my_band) {
-                        const unsigned slot = atomicAdd(cand_count, 1u);
-                        if (slot < cand_cap) {
-                            TensorCand cnd;
-                            cnd.q = (int)q; cnd.unit = (t0 + t) * (T_BN / 32) + c; cnd.smin = cmin[c];
-                            cand[slot] = cnd;
-                        }
-                        if (cmin[c] < run_min) {
-                            run_min = cmin[c];
-                            atomicMin(approx_min + q, f2ord(run_min));
-                        }
-                    }
+            c0 = fminf(c0, __uint_as_float(cur[7]));
+            c1 = fminf(c1, __uint_as_float(cur[15]));
+            c2 = fminf(c2, __uint_as_float(cur[23]));
+            c3 = fminf(c3, __uint_as_float(cur[31]));
+            const float cm = fminf(min3(c0, c1, c2), c3);
+#endif
+            // candidates have 32-reference granularity (one TMEM chunk): 4x less to re-score than a tile
+            if (NNS_T_EXPERIMENT < 2 && cm <= thresh) {
+                TensorCand cnd;
+                cnd.q = (int)q; cnd.unit = (t0 + t) * (T_BN / 32) + c; cnd.smin = cm;
+                cand_emit(cb, s_cand_count, cta, cnd);
+                if (cm < run_min) {
+                    run_min = cm;
+                    thresh = run_min + my_band;
+                    atomicMin(approx_min + q, f2ord(run_min));
                 }
+            }
+        };
+        for (int t = (T_TEAMS == 2 ? team : 0); t < nt; t += T_TEAMS) {
+            const int buf = t & 1;
+            const uint32_t taddr = lane_base + (uint32_t)(buf * 2 * T_BN);
+            mbar_wait_hot(acc_full + 8 * buf, (uint32_t)((t >> 1) & 1));
+            if (lane == 0) T_TRACE(4 + e, t);
+            tc_fence_after();
+            // The chunk loop is deliberately NOT unrolled: unrolled, ptxas hoists all four loads to the
+            // top of the tile and spills the loop invariants to make room for 128 destination registers.
+#pragma unroll 1
+            for (int c = 0; c < T_CPW; ++c) {
+                tmem_ld32(taddr + c * 32, v[0]);
+                tmem_ld_wait();
+                if (c + 1 == T_CPW) {
+                    // every TMEM read of this warp for tile t has completed: hand the accumulator back
+                    // to the MMA issuer before reducing the last chunk
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                    if (lane == 0) T_TRACE(4 + 16 + e, t);
+                }
+                reduce_chunk(v[0], t, c);
             }
         }
+#if NNS_T_EXPERIMENT >= 2
+#undef tmem_ld32
+#endif
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc512(tmem_base);
+    if (threadIdx.x == 0) {
+        const unsigned used = *s_cand_count;
+        cb.cta_count[cta] = min(used, cb.region_cap);
+        atomicAdd(cb.counters + 2, used);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact re-score: one warp per candidate (query, 128-reference block)
+// exact re-score: candidates are filtered against the FINAL approximate minimum by one lane each,
+// the survivors are evaluated by the whole warp, one lane per reference of the 32-reference unit
 // ---------------------------------------------------------------------------------------------
 template <bool EXACT>
 __global__ void __launch_bounds__(256)
 tensor_rescore_kernel(const float* __restrict__ queries, const int k, const float* __restrict__ blocks,
-                      const int index_base, const TensorCand* __restrict__ cand, const unsigned* __restrict__ cand_count,
-                      const unsigned cand_cap, const float* __restrict__ band, const unsigned* __restrict__ approx_min,
-                      u64* __restrict__ keys, int* __restrict__ overflow)
+                      const int index_base, const CandBuf cb, const float* __restrict__ band,
+                      const unsigned* __restrict__ approx_min, u64* __restrict__ keys)
 {
-    const unsigned total = *cand_count;
-    if (total > cand_cap) {  // the wide kernel takes over (launched right after with this flag)
-        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+    const unsigned common = cb.counters[0];
+    if (common > cb.common_cap || cb.counters[1] != 0u) {  // the FP32 kernel launched next takes over
+        if (blockIdx.x == 0 && threadIdx.x == 0) cb.counters[1] = 1u;
         return;
     }
     const int lane = (int)(threadIdx.x & 31);
     const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    // each lane tests one candidate against the final minimum; survivors are then re-scored one at
-    // a time by the whole warp, one lane per reference of the 32-reference unit
-    for (unsigned base = wid * 32; base < total; base += nw * 32) {
-        const unsigned ci = base + lane;
+    const unsigned gpr = cb.region_cap / 32;                   // 32-record groups per CTA region
+    const unsigned region_groups = cb.n_ctas * gpr;
+    const unsigned groups = region_groups + (common + 31) / 32;
+    for (unsigned gi = wid; gi < groups; gi += nw) {
+        size_t first;
+        unsigned count;
+        if (gi < region_groups) {
+            const unsigned cta = gi / gpr, s0 = (gi - cta * gpr) * 32;
+            const unsigned used = cb.cta_count[cta];
+            if (s0 >= used) continue;
+            first = (size_t)cta * cb.region_cap + s0;
+            count = min(32u, used - s0);
+        } else {
+            const unsigned s0 = (gi - region_groups) * 32;
+            first = (size_t)cb.n_ctas * cb.region_cap + s0;
+            count = min(32u, common - s0);
+        }
         TensorCand mine;
         mine.q = 0; mine.unit = 0; mine.smin = 0.0f;
         bool live = false;
-        if (ci < total) {
-            mine = cand[ci];
+        if ((unsigned)lane < count) {
+            mine = cb.rec[first + lane];
             live = mine.smin <= ord2f(approx_min[mine.q]) + band[mine.q];
         }
         unsigned mask = __ballot_sync(0xffffffffu, live);
@@ -576,22 +726,24 @@ cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_s
     return cudaGetLastError();
 }
 
-int tensor_stages(const TensorGeom& g) { return g.KB == 2 ? 4 : g.KB == 1 ? 6 : g.KS == 2 ? 16 : 24; }
+// reference tiles per TMA stage / ring depth per operand geometry (stage = G tiles <= 36 KiB)
+static int tensor_group(const TensorGeom& g) { return g.KB == 0 ? (g.KS == 1 ? 4 : 2) : 1; }
+static int tensor_stages(const TensorGeom& g) { return g.KB == 2 ? 4 : g.KB == 1 ? (g.KS == 0 ? 8 : 6) : 6; }
 
-size_t tensor_smem_bytes(const TensorGeom& g)
+static size_t tensor_smem_bytes(const TensorGeom& g)
 {
-    return image_bytes(T_BM, g.KB, g.KS) + (size_t)tensor_stages(g) * image_bytes(T_BN, g.KB, g.KS) +
+    return image_bytes(T_BM, g.KB, g.KS) + (size_t)tensor_stages(g) * tensor_group(g) * image_bytes(T_BN, g.KB, g.KS) +
            (2 * T_MAX_STAGES + 8) * 8 + 16;
 }
 
-template <int KB, int KS, int STAGES>
+template <int KB, int KS, int STAGES, int G>
 static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
                                         const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
-                                        TensorCand* cand, unsigned* cnt, unsigned cand_cap)
+                                        const CandBuf& cb)
 {
-    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_screen_kernel<KB, KS, STAGES><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cand, cnt, cand_cap);
+    tensor_screen_kernel<KB, KS, STAGES, G><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb);
     return cudaGetLastError();
 }
 
@@ -624,27 +776,41 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     const int tps = (nblocks + splits - 1) / splits;
     splits = (nblocks + tps - 1) / tps;
 
-    // stream-ordered scratch: query image, band, approx_min, candidates, counters.  Every split of
-    // a strip emits at least its first tile per query, then running-minimum records + the band.
+    // Candidate capacity.  Every split of a strip emits its first tiles per query, then one record
+    // per running-minimum improvement (~ln tiles) and per unit inside the band: a CTA region holds
+    // 64 / splits + 6 records per query, the common spill region another m + 65536.
+    CandBuf cb{};
+    cb.n_ctas = (unsigned)strips * (unsigned)splits;
+    if (tiny_candidate_buffer) {  // test hook: forces the overflow -> wide-kernel fallback
+        cb.region_cap = 32;
+        cb.common_cap = 32;
+    } else {
+        size_t region = ((size_t)T_BM * 64 / splits + (size_t)T_BM * 6 + 31) & ~(size_t)31;
+        const size_t max_records = (size_t)1 << 30;
+        if (region * cb.n_ctas > max_records) region = std::max<size_t>(32, (max_records / cb.n_ctas) & ~(size_t)31);
+        cb.region_cap = (unsigned)region;
+        cb.common_cap = (unsigned)std::min<size_t>((size_t)m + 65536, (size_t)1 << 28);
+    }
+    const size_t cand_records = (size_t)cb.n_ctas * cb.region_cap + cb.common_cap;
+
+    // stream-ordered scratch: query image, band, approx_min, counters, per-CTA counts, candidates
     const size_t qimg_bytes = (size_t)strips * image_bytes(T_BM, g.KB, g.KS);
-    const unsigned cand_cap = tiny_candidate_buffer
-                                  ? 64u  // test hook: forces the overflow -> wide-kernel fallback
-                                  : (unsigned)std::min<size_t>((size_t)m * (64 + 6 * (size_t)splits) + 65536, (size_t)1 << 30);
     const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
     const size_t off_amin = off_band + (((size_t)m * 4 + 255) & ~(size_t)255);
     const size_t off_cnt = off_amin + (((size_t)m * 4 + 255) & ~(size_t)255);
-    const size_t off_cand = off_cnt + 256;
-    const size_t total = off_cand + (size_t)cand_cap * sizeof(TensorCand);
+    const size_t off_ccnt = off_cnt + 256;
+    const size_t off_cand = off_ccnt + (((size_t)cb.n_ctas * 4 + 255) & ~(size_t)255);
+    const size_t total = off_cand + cand_records * sizeof(TensorCand);
     unsigned char* scratch = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&scratch, total, st);
     if (e != cudaSuccess) return e;
     float* band = reinterpret_cast<float*>(scratch + off_band);
     unsigned* amin = reinterpret_cast<unsigned*>(scratch + off_amin);
-    unsigned* cnt = reinterpret_cast<unsigned*>(scratch + off_cnt);
-    int* overflow = reinterpret_cast<int*>(cnt + 1);
-    TensorCand* cand = reinterpret_cast<TensorCand*>(scratch + off_cand);
+    cb.counters = reinterpret_cast<unsigned*>(scratch + off_cnt);
+    cb.cta_count = reinterpret_cast<unsigned*>(scratch + off_ccnt);
+    cb.rec = reinterpret_cast<TensorCand*>(scratch + off_cand);
 
-    e = cudaMemsetAsync(cnt, 0, 256, st);
+    e = cudaMemsetAsync(cb.counters, 0, 256, st);
     if (e == cudaSuccess) {
         tensor_query_image_kernel<<<strips, 256, 0, st>>>(d_queries, m, k, g, hdr, scratch, band, amin);
         e = cudaGetLastError();
@@ -654,37 +820,32 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         // CTA is resident per SM even at KP = 64
         const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
         dim3 grid((unsigned)strips, (unsigned)splits);
-        if (g.KB == 0 && g.KS == 1) e = tensor_screen_launch<0, 1, 24>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
-        else if (g.KB == 0) e = tensor_screen_launch<0, 2, 16>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
-        else if (g.KB == 1) e = tensor_screen_launch<1, 1, 6>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
-        else e = tensor_screen_launch<2, 1, 4>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cand, cnt, cand_cap);
+#define NNS_SCREEN(KB_, KS_, ST_, G_) \
+    tensor_screen_launch<KB_, KS_, ST_, G_>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cb)
+        if (g.KB == 0 && g.KS == 1) e = NNS_SCREEN(0, 1, 6, 4);
+        else if (g.KB == 0) e = NNS_SCREEN(0, 2, 6, 2);
+        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1);
+        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 6, 1);
+        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 4, 1);
+        else e = NNS_SCREEN(2, 1, 4, 1);
+#undef NNS_SCREEN
     }
     if (e == cudaSuccess) {
         const int rgrid = num_sms * 8;
         if (exact)
-            tensor_rescore_kernel<true><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cand, cnt, cand_cap, band, amin, d_keys, overflow);
+            tensor_rescore_kernel<true><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cb, band, amin, d_keys);
         else
-            tensor_rescore_kernel<false><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cand, cnt, cand_cap, band, amin, d_keys, overflow);
+            tensor_rescore_kernel<false><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cb, band, amin, d_keys);
         e = cudaGetLastError();
     }
+    if (launches) *launches = 3;
+    // d_stats: [0] candidates emitted, [1] overflow flag (the caller launches the FP32 fallback kernel with
+    // it as its enable flag), [2] candidate capacity
     if (e == cudaSuccess) {
-        // overflow fallback: the wide kernel runs only if the device flag is set
-        WideArgs a{};
-        a.queries = d_queries; a.m = m; a.k = k; a.blocks = d_blocks; a.nblocks = nblocks;
-        a.nqg = (m + WIDE_QT - 1) / WIDE_QT;
-        int s = 1;
-        if (a.nqg < 4 * num_sms * 8) s = std::max(1, std::min((nblocks + 1) / 2, (4 * num_sms * 8 + a.nqg - 1) / a.nqg));
-        if (s > 65535) s = 65535;
-        a.blocks_per_split = (nblocks + s - 1) / s;
-        a.splits = (nblocks + a.blocks_per_split - 1) / a.blocks_per_split;
-        a.index_base = index_base; a.keys = d_keys; a.stream = st; a.enable = overflow;
-        e = wide_launch(exact, a);
-    }
-    if (launches) *launches = 4;
-    // diagnostics: [0] candidates emitted, [1] overflow flag, [2] candidate capacity
-    if (e == cudaSuccess && d_stats) {
-        e = cudaMemcpyAsync(d_stats, cnt, 2 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stats + 2, &cand_cap, sizeof(unsigned), cudaMemcpyHostToDevice, st);
+        const unsigned cap = (unsigned)std::min<size_t>(cand_records, 0xffffffffu);
+        e = cudaMemcpyAsync(d_stats, cb.counters + 2, sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stats + 1, cb.counters + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stats + 2, &cap, sizeof(unsigned), cudaMemcpyHostToDevice, st);
     }
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;

@@ -15,7 +15,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint, c_uint64
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libnns_b200.so")
+# NNS_B200_LIB: another build of the same library (tools/tensor_tune.sh's kernel variants)
+LIB_PATH = os.environ.get("NNS_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libnns_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, 1, 2, 3, 4
 REF_BLOCK = 128
@@ -126,6 +127,23 @@ def plan(k: int, m: int, n: int, flags: int = 0, num_sms: int = 148) -> dict:
     _check(lib.nns_b200_plan(k, m, n, flags, num_sms, p))
     names = ("path", "q", "warps", "stages", "query_blocks", "splits", "blocks_per_split", "smem")
     return dict(zip(names, list(p)))
+
+
+def tensor_kp(k: int) -> int:
+    """Contraction length (BF16 columns) the tcgen05 screen uses for dimension k: mirror of
+    tensor_geom() in csrc/tensor_search.cu (3k split-precision columns up to k = 42, + 3 norm columns)."""
+    ndata = 3 * k if k <= 42 else k
+    if ndata + 3 <= 16:
+        return 16
+    if ndata + 3 <= 32:
+        return 32
+    if ndata + 3 <= 64:
+        return 64
+    if ndata <= 64:
+        return 80
+    if ndata + 3 <= 128:
+        return 128
+    return 144
 
 
 def tensor_stats() -> dict:

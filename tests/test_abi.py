@@ -40,22 +40,44 @@ def test_header_constants_match_binding(nns):
     assert nns.KEY_INIT >> 32 == np.array([np.inf], np.float32).view(np.uint32)[0]
 
 
+def tensor_geometry(k):
+    """Mirror of tensor_geom() in csrc/tensor_search.cu: (64-column swizzled blocks, 16-column steps)."""
+    ndata = 3 * k if k <= 42 else k  # split-precision BF16 columns up to k = 42
+    if ndata + 3 <= 16:
+        return 0, 1
+    if ndata + 3 <= 32:
+        return 0, 2
+    if ndata + 3 <= 64:
+        return 1, 0
+    if ndata <= 64:
+        return 1, 1
+    if ndata + 3 <= 128:
+        return 2, 0
+    return 2, 1
+
+
 def test_index_geometry(nns):
-    # 32-float header + (k coordinate rows + 1 norm row) x 128 lanes per block of 128 points
+    # 32-float header + (k coordinate rows + 1 norm row) x 128 lanes per block of 128 points, then (k <= 128)
+    # the tensor section: 256-float header + per block a BF16 operand image of 128 rows x (KB * 128 + KS * 32) B
+    def floats(k, n):
+        if n <= 0:
+            return 0
+        nb = (n + 127) // 128
+        total = 32 + nb * (k + 1) * 128
+        if k <= 128:
+            kb, ks = tensor_geometry(k)
+            total += 256 + nb * 128 * (kb * 128 + ks * 32) // 4
+        return total
+
     assert nns.index_floats(3, 0) == 0
-    ts = lambda kp, nb: 256 + nb * (kp * 128 * 2 + 128 * 32) // 4  # tensor section (k <= 128)
-    assert nns.index_floats(3, 1) == 32 + 4 * 128 + ts(64, 1)
-    assert nns.index_floats(3, 129) == 32 + 2 * 4 * 128 + ts(64, 2)
-    assert nns.index_floats(16, 16777216) == 32 + 17 * 16777216 + ts(64, 131072)
-    # 32 < k <= 128: + tensor section (256-float header, |r'|^2 per lane, BF16 image padded to 64/128 dims)
-    # tensor section: 256-float header + per block a BF16 image (KP x 128 x 2 B) + the extra K step (128 x 32 B)
-    assert nns.index_floats(128, 128) == 32 + 129 * 128 + 256 + (128 * 128 * 2 + 128 * 32) // 4
-    assert nns.index_floats(40, 129) == 32 + 2 * 41 * 128 + 256 + 2 * (128 * 128 * 2 + 128 * 32) // 4  # split: 120 columns
-    assert nns.index_floats(50, 129) == 32 + 2 * 51 * 128 + 256 + 2 * (64 * 128 * 2 + 128 * 32) // 4  # plain BF16: 50 columns
-    assert nns.index_floats(129, 128) == 32 + 130 * 128
-    # k <= 42: split-precision image, 3k columns padded to 64 / 128
-    assert nns.index_floats(3, 128) == 32 + 4 * 128 + 256 + (64 * 128 * 2 + 128 * 32) // 4
-    assert nns.index_floats(22, 128) == 32 + 23 * 128 + 256 + (128 * 128 * 2 + 128 * 32) // 4
+    assert [tensor_geometry(k) for k in (1, 3, 4, 5, 9, 10, 16, 20, 21, 41, 42, 43, 61, 62, 64, 65, 125, 126, 128)] == [
+        (0, 1), (0, 1), (0, 1), (0, 2), (0, 2), (1, 0), (1, 0), (1, 0), (1, 1), (2, 0), (2, 1), (1, 0), (1, 0), (1, 1),
+        (1, 1), (2, 0), (2, 0), (2, 1), (2, 1)]
+    for k, n in [(3, 1), (3, 129), (16, 16777216), (128, 128), (40, 129), (50, 129), (129, 128), (3, 128), (22, 128),
+                 (4, 1000), (5, 1000), (10, 77), (21, 4096), (64, 300), (200, 5)]:
+        assert nns.index_floats(k, n) == floats(k, n), (k, n)
+    assert nns.index_floats(3, 1) == 32 + 4 * 128 + 256 + 128 * 32 // 4  # k = 3: one K = 16 step per reference
+    assert nns.index_floats(129, 128) == 32 + 130 * 128                  # k > 128: no tensor section
     assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= (32 + 2 * 4 * 128) * 4 + 80
 
 
@@ -85,7 +107,13 @@ def test_no_cpu_fallback_fails_loudly_without_gpu(nns):
 
 
 def test_plan_paths(nns):
-    p = nns.plan(3, 65536, 4194304)  # BASELINE config C2
+    # BASELINE config C2: large enough for the split-precision tcgen05 screen (strips of 256 queries) ...
+    p = nns.plan(3, 65536, 4194304)
+    assert p["path"] == 2 and p["query_blocks"] == 256
+    assert nns.plan(16, 262144, 16777216)["path"] == 2  # ... and so is C3
+    assert nns.plan(3, 1024, 65536)["path"] == 0        # C1 is not: register-blocked FP32 kernel
+    assert nns.plan(3, 65536, 4194304, nns.FLAG_EXACT_FORM)["path"] == 0  # V0's formulation is FP32-only
+    p = nns.plan(3, 65536, 4194304, nns.FLAG_FORCE_LOWK)  # the FP32 kernel for the same shape
     assert p["path"] == 0 and p["q"] in (4, 8) and p["warps"] == 8
     assert p["splits"] * p["blocks_per_split"] >= 4194304 // 128
     assert (p["splits"] - 1) * p["blocks_per_split"] < 4194304 // 128  # no empty split
@@ -105,7 +133,7 @@ def test_plan_paths(nns):
 @pytest.mark.parametrize("m,n", [(16, 1), (1000, 127), (1024, 65536), (65536, 4194304), (300000, 1000), (16777216, 16777216)])
 def test_plan_covers_every_reference_block_and_query(nns, k, m, n):
     for q_over in (0,):
-        p = nns.plan(k, m, n, nns.flag_overrides(q=q_over))
+        p = nns.plan(k, m, n, nns.flag_overrides(q=q_over) | nns.FLAG_FORCE_LOWK)
         nblocks = (n + 127) // 128
         assert p["path"] == 0
         assert p["query_blocks"] * 32 * p["warps"] * p["q"] >= m
@@ -116,7 +144,7 @@ def test_plan_covers_every_reference_block_and_query(nns, k, m, n):
 
 
 def test_plan_overrides(nns):
-    p = nns.plan(3, 65536, 4194304, nns.flag_overrides(q=8, warps=4, stages=3))
+    p = nns.plan(3, 65536, 4194304, nns.flag_overrides(q=8, warps=4, stages=3) | nns.FLAG_FORCE_LOWK)
     assert (p["q"], p["warps"], p["stages"]) == (8, 4, 3)
     with pytest.raises(nns.NnsError):
-        nns.plan(3, 65536, 4194304, nns.flag_overrides(q=5))
+        nns.plan(3, 65536, 4194304, nns.flag_overrides(q=5) | nns.FLAG_FORCE_LOWK)
