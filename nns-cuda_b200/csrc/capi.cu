@@ -290,6 +290,15 @@ static int ctx_get(int device, DeviceCtx** out)
                         device, prop.major, prop.minor);
         }
         c->num_sms = prop.multiProcessorCount;
+        // the tensor path takes its scratch (query image, candidate records) from the stream-ordered
+        // allocator; keep freed blocks in the pool across synchronisations instead of returning
+        // ~100 MB to the driver after every host-pointer call
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
         CU_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
         c->ready = true;
