@@ -103,6 +103,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: only later samples count (nvidia-smi needs a few hundred ms to
+        deliver its first line, so the sampler is started before the warm-up steps)."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -114,7 +119,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        first = getattr(self, "first", 0)
+        window = self.lines[first:]
+        note = None
+        if len(window) < 2:  # timed region shorter than the sampling period: use the warm-up samples too
+            window, note = self.lines[max(0, first - 5):], "timed region shorter than 2 sampling periods: includes warm-up samples"
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -127,8 +137,11 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw)}
+        out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+               "samples": len(sm), "power_w_max": max(pw)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_reference_rate(k, n, s_sample, r, steps=1):
@@ -276,19 +289,20 @@ def main():
             dist.all_reduce(keys, op=dist.ReduceOp.MIN)  # packed (dist, idx) keys: exact lowest-index merge
         return nns_b200.unpack_keys(keys, m, stream)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         flush.zero_()
         idx = step()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = nns_b200.launch_count()
-    sampler.start()
+    sampler.mark()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event brackets)
@@ -371,7 +385,7 @@ def main():
                     "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s}
         if clocks.get("sm_mhz"):
             roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
-        if not (args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING)) and m >= 16:
+        if not (args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING)) and m >= 16 and world == 1:
             roofline["exact_form_kernel"] = exact_form_side_measurement()
     elif path == 2 and k <= 32:
         # Split-precision tcgen05 screen for low k: the contraction is 16-64 BF16 columns,
@@ -397,7 +411,8 @@ def main():
                     "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": nns_b200.tensor_stats()}
         if clocks.get("sm_mhz"):
             roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
-        roofline["exact_form_kernel"] = exact_form_side_measurement()
+        if world == 1:
+            roofline["exact_form_kernel"] = exact_form_side_measurement()
     elif path == 2:
         # tcgen05 path: 2k FLOPs per pair (the -2 q.r contraction only; norms, epilogue and the exact
         # re-score count as zero) against the measured dense BF16 peak

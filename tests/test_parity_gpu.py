@@ -292,6 +292,38 @@ def test_full_size_c2_properties(nns, oracle, torch_mod):
     assert np.array_equal(n - 1 - grev, g)
 
 
+@pytest.mark.parametrize("name,k,m,n,nsample", [("C3", 16, 262144, 16777216, 48), ("C4", 128, 1048576, 1048576, 96)])
+def test_full_size_c3_c4_properties(nns, oracle, torch_mod, name, k, m, n, nsample):
+    """BASELINE configs C3 (k=16, m=262,144, n=16,777,216) and C4 (k=128, m=n=1,048,576) at full size
+    on the tcgen05 path the planner picks for them: (a) a seeded sample of queries against V0 over the
+    FULL reference set, (b) idempotence of the packed-key minimum, (c) searching the two halves of
+    the reference set separately (index_base) and min-merging the keys equals the one-shot search
+    bit for bit, (d) C3: the FP32 screened kernel returns the same (dist, idx) keys, (e) the screen
+    stayed selective (no overflow, a few dozen candidates per query)."""
+    torch = torch_mod
+    s, r = make_case("uniform", k, m, n, 1000)
+    dq, dr = dev(torch, s), dev(torch, r)
+    index = nns.DeviceIndex(dr)
+    assert nns.plan(k, m, n)["path"] == 2
+    keys = index.search_keys(dq, index.new_keys(m))
+    torch.cuda.synchronize()
+    st = nns.tensor_stats()
+    assert st["overflow"] == 0 and st["candidates"] < 64 * m, st
+    again = index.search_keys(dq, keys.clone())
+    assert torch.equal(again, keys)
+    half = (n // 2 // 128) * 128
+    lo, hi = nns.DeviceIndex(dr[:half].contiguous()), nns.DeviceIndex(dr[half:].contiguous(), index_base=half)
+    merged = hi.search_keys(dq, lo.search_keys(dq, index.new_keys(m)))
+    assert torch.equal(merged, keys)
+    if k <= 32:
+        assert torch.equal(index.search_keys(dq, index.new_keys(m), nns.FLAG_FORCE_LOWK), keys)
+    g = nns.unpack_keys(keys, m).cpu().numpy()
+    sample = np.random.default_rng(1000).permutation(m)[:nsample]
+    v, _ = oracle.v0_omp(k, nsample, n, s[sample], r)
+    rep = oracle.check_tie_rule(k, nsample, n, s[sample], r, g[sample], v, REL_TOL)
+    assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= nsample - 1, rep
+
+
 def test_search_multi_on_every_visible_gpu(nns, oracle, torch_mod):
     """nns_b200_search_multi (one process, host thread per GPU): both shardings return V0's answer
     for every GPU count; needs >= 2 visible GPUs to be more than a smoke test."""
