@@ -364,7 +364,9 @@ def main():
         return {"kernel_ms": x_ms, "kernel_pairs_per_s": x_rate, "executed_lane_slots_per_pair": 2 * k,
                 "frac": x_rate * 2.0 * k / lane_peak}
 
-    if path == 0:
+    tstats = nns_b200.tensor_stats() if path == 2 else None
+    fell_back = bool(tstats and tstats["overflow"])  # the screen ran out of candidate space: the FP32 kernel did the work
+    if path == 0 or (fell_back and k <= 32):
         # Executed FP32 lane-slots per pair: the screened kernel evaluates
         # s = |r|^2 - 2q.r with k FMAs per pair; the exact-form kernel runs V0's k subtractions +
         # k FMAs (2k; 3k with separately rounded mul/add).  `frac` is computed from the slots the
@@ -376,6 +378,9 @@ def main():
             slots, form = 2 * k, "exact form (FADD2 + FFMA2 per dimension)"
         else:
             slots, form = k, "norm-expansion screen (FFMA2 per dimension) + exact evaluation of survivors"
+        if fell_back:
+            form += ("; the tcgen05 screen planned for this shape overflowed its candidate buffer on this data "
+                     "(dense near-ties) and handed over on the device -- the time includes the aborted screen")
         achieved = kern_pairs_per_s * slots * 2.0 / 1e12
         roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak_tflops, "traffic": None,
@@ -383,32 +388,42 @@ def main():
                     "v0_form_frac": kern_pairs_per_s * 2.0 * k / lane_peak,
                     "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz ({pk_src} sm_max_mhz; FP32 peak is not in MEASURED_PEAKS.json)",
                     "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s}
+        if tstats:
+            roofline["tensor_stats"] = tstats
         if clocks.get("sm_mhz"):
             roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
         if not (args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING)) and m >= 16 and world == 1:
             roofline["exact_form_kernel"] = exact_form_side_measurement()
     elif path == 2 and k <= 32:
-        # Split-precision tcgen05 screen for low k: the contraction is 16-64 BF16 columns,
-        # so the tensor pipe idles and what every pair still costs is ONE minimum on the 128-lane/clk/SM
-        # ALU pipe (FMNMX3 retires two new values per instruction at half rate) in the epilogue that
-        # reduces the TMEM accumulators.  SURVEY.md 8(d): a kernel that executes fewer than V0's 2k
-        # lane-slots per pair is priced at the slots it executes -> 1 per pair, against the same
-        # 128 lanes x 148 SMs x f peak as the FP32 kernels.  The tensor-pipe fractions are reported
-        # beside it: `tensor_frac` counts the algorithmic 2k FLOPs per pair, `tensor_frac_executed`
-        # the 2 x padded-contraction FLOPs the MMAs really perform.
+        # Split-precision tcgen05 screen for low k.  Two resources can bind it:
+        #  * the ALU pipe: every pair costs ONE minimum in the epilogue that reduces the TMEM accumulators
+        #    (FMNMX3 retires two new values per instruction at half rate: 128 pairs/clk/SM, the same lane
+        #    rate as the FP32 pipe).  SURVEY.md 8(d): a kernel that executes fewer than V0's 2k lane-slots
+        #    per pair is priced at the slots it executes -> 1 per pair against 128 lanes x 148 SMs x f;
+        #  * the tensor pipe, once the contraction is long enough (k = 16: 3k + 3 columns padded to 64):
+        #    algorithmic work 2k FLOPs per pair against the measured BF16 peak; the hi/lo column triples
+        #    and the padding are real MMA work but count as zero (`tensor_frac_executed` shows them).
+        # The line reports the one with the higher utilisation as `bound`, the other beside it.
         kp = nns_b200.tensor_kp(k)
-        achieved = kern_pairs_per_s * 1 * 2.0 / 1e12
-        roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak_tflops, "traffic": None,
-                    "kernel": "tcgen05 split-precision BF16 screen (K = %d columns) + query image + exact FP32 re-score; "
-                              "bound by one FMNMX3 lane-slot per pair in the TMEM epilogue" % kp,
-                    "executed_lane_slots_per_pair": 1,
-                    "v0_form_frac": kern_pairs_per_s * 2.0 * k / lane_peak,
-                    "tensor_frac": kern_pairs_per_s * 2.0 * k / 1e12 / bf16_peak,
-                    "tensor_frac_executed": kern_pairs_per_s * 2.0 * kp / 1e12 / bf16_peak,
-                    "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz ({pk_src} sm_max_mhz; the ALU-pipe lane rate "
-                                   f"equals the FP32 lane rate; bf16_tflops {pk_src})",
-                    "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": nns_b200.tensor_stats()}
+        alu_frac = kern_pairs_per_s * 1.0 / lane_peak
+        tensor_frac = kern_pairs_per_s * 2.0 * k / 1e12 / bf16_peak
+        tensor_exec = kern_pairs_per_s * 2.0 * kp / 1e12 / bf16_peak
+        kernel = ("tcgen05 split-precision BF16 screen (K = %d columns for k = %d) + query image + exact FP32 re-score" % (kp, k))
+        if alu_frac >= tensor_exec:
+            roofline = {"bound": "fp32", "achieved": kern_pairs_per_s * 2.0 / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                        "frac": alu_frac, "traffic": None,
+                        "kernel": kernel + "; bound by one FMNMX3 lane-slot per pair in the TMEM epilogue",
+                        "executed_lane_slots_per_pair": 1,
+                        "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz ({pk_src} sm_max_mhz; the ALU-pipe lane rate "
+                                       f"equals the FP32 lane rate)"}
+        else:
+            roofline = {"bound": "tensor", "achieved": kern_pairs_per_s * 2.0 * k / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                        "frac": tensor_frac, "traffic": None,
+                        "kernel": kernel + "; bound by the tensor pipe, which executes %.1fx the algorithmic FLOPs" % (kp / k),
+                        "peak_source": f"{pk_src} bf16_tflops (burst, cuBLAS 8192^3)"}
+        roofline.update({"alu_min_frac": alu_frac, "tensor_frac": tensor_frac, "tensor_frac_executed": tensor_exec,
+                         "v0_form_frac": kern_pairs_per_s * 2.0 * k / lane_peak,
+                         "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": tstats})
         if clocks.get("sm_mhz"):
             roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
         if world == 1:
@@ -420,7 +435,7 @@ def main():
         roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
                     "traffic": None, "peak_source": f"{pk_src} bf16_tflops (burst, cuBLAS 8192^3)",
                     "kernel": "tcgen05 BF16 screen (K = %d columns) + query image + exact FP32 re-score" % nns_b200.tensor_kp(k),
-                    "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": nns_b200.tensor_stats()}
+                    "kernel_ms": kern_ms_avg, "kernel_pairs_per_s": kern_pairs_per_s, "tensor_stats": tstats}
         if clocks.get("sm_mhz"):
             roofline["frac_at_sampled_clock"] = roofline["frac"] * sm_max_mhz / clocks["sm_mhz"]
     else:
@@ -439,7 +454,7 @@ def main():
                         "peak_source": f"derived 2*128 lanes*148 SMs*{sm_max_mhz:.0f} MHz"}
 
     if world == 1:
-        pname = {0: "lowk", 1: "wide", 2: "tensor"}[path]
+        pname = {0: "lowk", 1: "wide", 2: "tensor"}[0 if (fell_back and k <= 32) else path]
         if args.flags & (nns_b200.FLAG_EXACT_FORM | nns_b200.FLAG_V0_ROUNDING):
             pname += "_exact"
         roofline["traffic"] = ncu_traffic(name, pname)
