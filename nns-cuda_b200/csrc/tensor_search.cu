@@ -54,6 +54,9 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #ifndef NNS_T_TEAMS
 #define NNS_T_TEAMS 2       // epilogue teams of 8 warps; team i owns TMEM buffer i and reduces the tiles t % 2 == i
 #endif
+#ifndef NNS_T_LD64
+#define NNS_T_LD64 0        // 1: the epilogue reads 64 TMEM columns per load (two round trips per tile instead of four)
+#endif
 #ifndef NNS_T_SPIN
 #define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
 #endif
@@ -116,6 +119,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
+// true in exactly one (the lowest active) lane of the warp; must be called with all 32 lanes converged
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -481,37 +500,60 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ONE thread issues every MMA of the CTA, and for short contractions its own instruction
+        // stream paces the tile pipeline (ncu source view of the first two-team build: ~550 clk per
+        // tile of dependent uniform-datapath arithmetic, ~10 clk per instruction, and an
+        // ELECT / branch wrapper of ~45 clk around every tcgen05 instruction issued under
+        // `lane == 0`).  Hence: the thread is chosen with elect.sync (ptxas then knows that exactly one
+        // thread is active), every descriptor is built once before the loop (per tile only the 14-bit
+        // start-address field of the B descriptors moves), and the loop is unrolled over the two
+        // TMEM buffers so that buffer addresses and barrier addresses are immediates.
+        if (elect_one_sync()) {
             mbar_wait(a_full, 0);
+            const uint32_t a_addr = smem_u32(a_smem), b_addr0 = smem_u32(b_smem);
+            u64 adesc_sw[KB > 0 ? KB : 1][4][2], adesc_il[KS > 0 ? KS : 1][2];
+            uint32_t bdesc_sw_lo[KB > 0 ? KB : 1][4], bdesc_il_lo[KS > 0 ? KS : 1];
+            uint32_t bdesc_sw_hi = 0, bdesc_il_hi = 0;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const u64 bd = umma_desc_sw128(b_addr0 + kb * (T_BN * 128) + ks * 32);
+                    bdesc_sw_lo[kb][ks] = (uint32_t)bd;
+                    bdesc_sw_hi = (uint32_t)(bd >> 32);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) adesc_sw[kb][ks][h] = umma_desc_sw128(a_addr + kb * (T_BM * 128) + h * (128 * 128) + ks * 32);
+                }
+#pragma unroll
+            for (int x = 0; x < KS; ++x) {
+                const u64 bd = umma_desc_interleave(b_addr0 + B_MAIN + x * (2 * T_BN * 16), T_BN);
+                bdesc_il_lo[x] = (uint32_t)bd;
+                bdesc_il_hi = (uint32_t)(bd >> 32);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) adesc_il[x][h] = umma_desc_interleave(a_addr + A_MAIN + x * (2 * T_BM * 16) + h * (128 * 16), T_BM);
+            }
             int s = 0, j = 0;
             uint32_t ph = 0;
-            const uint32_t a_addr = smem_u32(a_smem);
-            for (int t = 0; t < nt; ++t) {
-                const int buf = t & 1;
+            uint32_t boff16 = 0;  // (byte offset of the current B tile inside the ring) >> 4: added to the descriptors' start-address field
+            auto issue_tile = [&](const int t, const int buf) {
                 mbar_wait_mma(acc_empty + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));  // its team drained this buffer
                 if (j == 0) mbar_wait_mma(b_full + 8 * s, ph);                      // TMA landed this stage
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(b_smem + (size_t)s * STAGE_BYTES + (size_t)j * B_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const u64 bdesc = umma_desc_sw128(b_addr + kb * (T_BN * 128) + ks * 32);
+                        const u64 bdesc = ((u64)bdesc_sw_hi << 32) | (u64)(bdesc_sw_lo[kb][ks] + boff16);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const u64 adesc = umma_desc_sw128(a_addr + kb * (T_BM * 128) + h * (128 * 128) + ks * 32);
-                            if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((kb | ks) != 0));
-                        }
+                        for (int h = 0; h < 2; ++h)
+                            if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc_sw[kb][ks][h], bdesc, T_IDESC, (uint32_t)((kb | ks) != 0));
                     }
-                }
 #pragma unroll
                 for (int x = 0; x < KS; ++x) {  // interleaved steps (the last columns carry |r'|^2)
-                    const u64 bdesc = umma_desc_interleave(b_addr + B_MAIN + x * (2 * T_BN * 16), T_BN);
+                    const u64 bdesc = ((u64)bdesc_il_hi << 32) | (u64)(bdesc_il_lo[x] + boff16);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const u64 adesc = umma_desc_interleave(a_addr + A_MAIN + x * (2 * T_BM * 16) + h * (128 * 16), T_BM);
-                        if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc, bdesc, T_IDESC, (uint32_t)((KB | x) != 0));
-                    }
+                    for (int h = 0; h < 2; ++h)
+                        if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc_il[x][h], bdesc, T_IDESC, (uint32_t)((KB | x) != 0));
                 }
                 tc_commit(acc_full + 8 * buf);   // accumulator complete
                 T_TRACE(3, t);
@@ -519,9 +561,15 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     tc_commit(b_empty + 8 * s);  // stage free once the MMAs of its tiles have read it
                     j = 0;
                     if (++s == T_STAGES) { s = 0; ph ^= 1u; }
+                    boff16 = (uint32_t)s * (STAGE_BYTES >> 4);
                 } else {
                     ++j;
+                    boff16 += B_BYTES >> 4;
                 }
+            };
+            for (int t = 0; t < nt; t += 2) {
+                issue_tile(t, 0);
+                if (t + 1 < nt) issue_tile(t + 1, 1);
             }
         }
     } else {
@@ -544,7 +592,11 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         // One TMEM chunk in flight per warp: with four epilogue warps per scheduler the load latency
         // of one warp is covered by the reductions of the other three.  (A register double buffer
         // measured no faster at k = 3 and slower at k = 128, where the box runs at its power cap.)
+#if NNS_T_LD64
+        uint32_t v[64];
+#else
         uint32_t v[1][32];
+#endif
 #if NNS_T_EXPERIMENT >= 2
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[0][i] = 0x7f800000u;
@@ -593,6 +645,21 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             tc_fence_after();
             // The chunk loop is deliberately NOT unrolled: unrolled, ptxas hoists all four loads to the
             // top of the tile and spills the loop invariants to make room for 128 destination registers.
+#if NNS_T_LD64
+#pragma unroll 1
+            for (int c = 0; c < T_CPW; c += 2) {
+                tmem_ld64(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (c + 2 == T_CPW) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                    if (lane == 0) T_TRACE(4 + 16 + e, t);
+                }
+                reduce_chunk(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), t, c);
+                reduce_chunk(*reinterpret_cast<const uint32_t(*)[32]>(&v[32]), t, c + 1);
+            }
+#else
 #pragma unroll 1
             for (int c = 0; c < T_CPW; ++c) {
                 tmem_ld32(taddr + c * 32, v[0]);
@@ -607,6 +674,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 }
                 reduce_chunk(v[0], t, c);
             }
+#endif
         }
 #if NNS_T_EXPERIMENT >= 2
 #undef tmem_ld32
