@@ -50,12 +50,12 @@ extern "C" {
                                         1.5x the FP32 work) instead of contracting to FMA   */
 #define NNS_B200_FLAG_FORCE_LOWK 2u  /* testing: force the register-blocked low-k kernel    */
 #define NNS_B200_FLAG_FORCE_WIDE 4u  /* testing: force the reference-parallel generic kernel */
-#define NNS_B200_FLAG_FORCE_TENSOR 8u /* testing: force the tcgen05 path (k multiple of 16) */
+#define NNS_B200_FLAG_FORCE_TENSOR 8u /* testing: force the tcgen05 screen + exact re-score (k <= 128) */
 #define NNS_B200_FLAG_EXACT_FORM 16u /* evaluate every pair in V0's subtract-square form (2k FP32
                                         lane-slots per pair) instead of screening pairs with the
                                         norm expansion and evaluating only the survivors that way;
                                         both return the same indices                          */
-#define NNS_B200_FLAG_TEST_TINY_CANDIDATES (1u << 28) /* testing: 64-entry candidate buffer in the
+#define NNS_B200_FLAG_TEST_TINY_CANDIDATES (1u << 28) /* testing: 32-record candidate regions in the
                                         tcgen05 path, forcing its overflow fallback              */
 /* bits 8-15 / 16-23 / 24-27: tuning overrides (queries per thread, warps per CTA, ring stages) */
 
@@ -124,12 +124,13 @@ int nns_b200_search_device(int k, int m, int n, const float *d_queries, const fl
 /* ---- host-side planning (pure function, no GPU needed; exported for tests) ----------------
  * Fills plan[0..7] = { path (0 = low-k, 1 = wide, 2 = tensor), queries per thread,
  * consumer warps per CTA, pipeline stages, query blocks, reference splits, reference blocks
- * per split, dynamic shared memory bytes } for a device with num_sms SMs. */
+ * per split, dynamic shared memory bytes } for a device with num_sms SMs.  Path 2 (tcgen05) reports
+ * 256-query strips as its query blocks; its reference splits are chosen at launch. */
 int nns_b200_plan(int k, int m, int n, unsigned flags, int num_sms, int *plan);
 
 /* diagnostics of the last tensor-path search on the current device (synchronises the device):
- * out3 = { (query, tile) candidates emitted by the tcgen05 screen, 1 if the candidate buffer
- * overflowed and the FP32 wide kernel redid the search, candidate capacity } */
+ * out3 = { (query, 32-reference unit) candidates emitted by the tcgen05 screen, 1 if the candidate
+ * buffer overflowed and the FP32 kernel launched behind it redid the search, candidate capacity } */
 int nns_b200_tensor_stats(unsigned *out3);
 
 /* number of kernels of this library launched by this process so far (bench.py's gpu_launches) */

@@ -353,32 +353,45 @@ static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_quer
         const float* d_section = d_blocks + (size_t)nblocks * index_block_floats(k);
         int launches = 0;
         ST_TRY(buf_reserve(&c->stats, 64));
-        CU_TRY(tensor_search(k, m, n, d_queries, d_blocks, d_section, index_base, d_keys, mode == LOWK_EXACT_V0,
-                             c->num_sms, st, &launches, (unsigned*)c->stats.p,
-                             (flags & NNS_B200_FLAG_TEST_TINY_CANDIDATES) != 0));
+        // per-call status words {candidates, overflow flag, capacity} from the stream-ordered pool: the
+        // flag gates the fallback kernel below, so it must not be shared with a search that another
+        // stream of this device has in flight
+        unsigned* d_status = nullptr;
+        CU_TRY(cudaMallocAsync((void**)&d_status, 64, st));
+        cudaError_t te = tensor_search(k, m, n, d_queries, d_blocks, d_section, index_base, d_keys, mode == LOWK_EXACT_V0,
+                                       c->num_sms, st, &launches, d_status, (flags & NNS_B200_FLAG_TEST_TINY_CANDIDATES) != 0);
         g_launches.fetch_add((unsigned long long)launches + 1, std::memory_order_relaxed);
         // Fallback for data whose near-ties overflow the candidate buffer (e.g. all points identical, or
         // clusters far denser than the BF16 screen resolves): the FP32 kernel of this shape, launched
-        // unconditionally behind the device-side flag the re-score kernel leaves in stats[1]; it
+        // unconditionally behind the device-side flag the re-score kernel leaves in d_status[1]; it
         // exits at once when the flag is clear.  No host round trip.
-        const int* enable = (const int*)c->stats.p + 1;
-        unsigned fb = (flags & ~(NNS_B200_FLAG_FORCE_TENSOR | NNS_B200_FLAG_TEST_TINY_CANDIDATES)) |
-                      ((k <= LOWK_MAX_K && m >= 16) ? NNS_B200_FLAG_FORCE_LOWK : NNS_B200_FLAG_FORCE_WIDE);
-        ST_TRY(make_plan(k, m, n, fb, c->num_sms, occ_query, c, &p));
-        if (p.path == 0) {
-            LowkArgs a{};
-            a.queries = d_queries; a.m = m; a.header = d_header; a.blocks = d_blocks; a.nblocks = nblocks;
-            a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
-            a.warps = p.warps; a.stages = p.stages; a.nqb = p.nqb; a.splits = p.splits; a.stream = st;
-            a.enable = enable;
-            CU_TRY(lowk_dispatch(k, p.q, mode, a, nullptr));
-        } else {
-            WideArgs a{};
-            a.queries = d_queries; a.m = m; a.k = k; a.blocks = d_blocks; a.nblocks = nblocks;
-            a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
-            a.nqg = p.nqb; a.splits = p.splits; a.stream = st; a.enable = enable;
-            CU_TRY(wide_launch(mode == LOWK_EXACT_V0, a));
+        int fst = NNS_B200_OK;
+        if (te == cudaSuccess) {
+            const int* enable = (const int*)d_status + 1;
+            unsigned fb = (flags & ~(NNS_B200_FLAG_FORCE_TENSOR | NNS_B200_FLAG_TEST_TINY_CANDIDATES)) |
+                          ((k <= LOWK_MAX_K && m >= 16) ? NNS_B200_FLAG_FORCE_LOWK : NNS_B200_FLAG_FORCE_WIDE);
+            fst = make_plan(k, m, n, fb, c->num_sms, occ_query, c, &p);
+            if (fst == NNS_B200_OK && p.path == 0) {
+                LowkArgs a{};
+                a.queries = d_queries; a.m = m; a.header = d_header; a.blocks = d_blocks; a.nblocks = nblocks;
+                a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
+                a.warps = p.warps; a.stages = p.stages; a.nqb = p.nqb; a.splits = p.splits; a.stream = st;
+                a.enable = enable;
+                te = lowk_dispatch(k, p.q, mode, a, nullptr);
+            } else if (fst == NNS_B200_OK) {
+                WideArgs a{};
+                a.queries = d_queries; a.m = m; a.k = k; a.blocks = d_blocks; a.nblocks = nblocks;
+                a.blocks_per_split = p.bps; a.index_base = index_base; a.keys = d_keys;
+                a.nqg = p.nqb; a.splits = p.splits; a.stream = st; a.enable = enable;
+                te = wide_launch(mode == LOWK_EXACT_V0, a);
+            }
+            // keep the last search's status words for nns_b200_tensor_stats()
+            if (te == cudaSuccess) te = cudaMemcpyAsync(c->stats.p, d_status, 3 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
         }
+        const cudaError_t fe = cudaFreeAsync(d_status, st);
+        ST_TRY(fst);
+        CU_TRY(te);
+        CU_TRY(fe);
         return NNS_B200_OK;
     }
     if (p.path == 0) {
