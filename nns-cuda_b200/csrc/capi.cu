@@ -77,11 +77,12 @@ struct Plan {
 // k <= 32: the split-precision tcgen05 screen (csrc/tensor_search.cu) beats the FP32 screened kernel
 // once the problem amortises its fixed cost (query image, four launches, per-CTA TMEM set-up):
 // B200, profiles/r1_tensor_*: C2 (k = 3, 2.7e11 pairs) 18.6 ms vs 39.9 ms, C3 (k = 16) 0.49 s vs 2.6 s,
-// C1 (6.7e7 pairs) 0.38 ms vs 0.064 ms.  Both paths return identical indices.
+// C1 (6.7e7 pairs) 0.38 ms vs 0.064 ms; the reference's largest shape (k = 16, m = 1024, n = 2^20,
+// 1.1e9 pairs) 8.1 ms vs 6.7 ms end to end.  Both paths return identical indices.
 static bool lowk_prefers_tensor(int k, int m, int n)
 {
     const double pairs = (double)m * (double)n;
-    return m >= 1024 && pairs >= (k <= 8 ? 4e9 : 1e9);
+    return m >= 1024 && pairs >= (k <= 8 ? 4e9 : 2e9);
 }
 
 typedef int (*occ_fn)(void* user, int k, int q, int mode, int warps, int stages);
