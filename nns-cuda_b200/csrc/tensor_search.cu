@@ -829,17 +829,29 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
 
     // reference splits: minimise (waves of one CTA per SM) x (tiles per CTA); every extra split
     // costs each query one more seed candidate, so ties go to fewer splits
-    int splits = 1;
-    {
+    auto choose_splits = [&](int smin) {
         double best = 1e300;
-        const int smax = std::min(nblocks, 64);
-        for (int sp = 1; sp <= smax; ++sp) {
+        int chosen = smin;
+        const int smax = std::max(std::min(nblocks, 64), std::min(nblocks, 2 * smin));
+        for (int sp = smin; sp <= smax; ++sp) {
             const int t = (nblocks + sp - 1) / sp;
             const int se = (nblocks + t - 1) / t;
             const double waves = (double)(((long long)strips * se + num_sms - 1) / num_sms);
             const double cost = waves * ((double)t + 24.0);  // + per-CTA prologue (A tile, TMEM alloc) in tile units
-            if (cost < best * 0.97) { best = cost; splits = se; }
+            if (cost < best * 0.97) { best = cost; chosen = se; }
         }
+        return chosen;
+    };
+    int splits = choose_splits(1);
+    // If the data overflows the candidate buffer, only the CTAs already running finish their share of
+    // the (then useless) pass -- the rest see the flag and exit.  A job of fewer than four waves is
+    // therefore cut into CTAs of at most 16384 tiles (tools/overflow_cost.py: +11 % instead of a whole
+    // wasted pass); such CTAs of one strip run concurrently, each from an unconverged minimum, so
+    // they get first-split sized candidate regions below.
+    bool short_ctas = false;
+    if ((long long)strips * splits < 4LL * num_sms && (nblocks + splits - 1) / splits > 16384) {
+        splits = choose_splits((nblocks + 16383) / 16384);
+        short_ctas = true;
     }
     const int tps = (nblocks + splits - 1) / splits;
     splits = (nblocks + tps - 1) / tps;
@@ -853,7 +865,7 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         cb.region_cap = 32;
         cb.common_cap = 32;
     } else {
-        size_t region = ((size_t)T_BM * 64 / splits + (size_t)T_BM * 6 + 31) & ~(size_t)31;
+        size_t region = short_ctas ? (size_t)T_BM * 40 : (((size_t)T_BM * 64 / splits + (size_t)T_BM * 6 + 31) & ~(size_t)31);
         const size_t max_records = (size_t)1 << 30;
         if (region * cb.n_ctas > max_records) region = std::max<size_t>(32, (max_records / cb.n_ctas) & ~(size_t)31);
         cb.region_cap = (unsigned)region;
