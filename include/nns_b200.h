@@ -73,6 +73,12 @@ void nns_b200_cudaCall(int k, int m, int n, float *s_points, float *r_points, in
 int nns_b200_search_host(int k, int m, int n, const float *s_points, const float *r_points,
                          int *results);
 
+/* nns_b200_search_host that also returns, per query, the FP32 squared distance to the reported
+ * neighbour (+INF when no reference has a distance below +INF, the case in which V0 reports index
+ * 0).  An extension: the reference's callback returns indices only (core.cu:52). */
+int nns_b200_search_host_dist(int k, int m, int n, const float *s_points, const float *r_points,
+                              int *results, float *distances);
+
 /* Single-process multi-GPU search over host arrays: replaces v8/v9::cudaCall's OpenMP
  * fan-out + host merge (core.cu:761-853, 965-1057).  shard_mode 0 = query-sharded (each GPU
  * gets a query slice and all references), 1 = reference-sharded (contiguous reference

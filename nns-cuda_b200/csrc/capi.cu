@@ -435,7 +435,7 @@ static unsigned host_flags();
 // index build + search of chunk c (compute stream); every chunk accumulates into the same
 // packed keys with its own index base.
 static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, const float* r, int index_base,
-                          u64* h_keys, int* h_idx, u64* ext_keys = nullptr)
+                          u64* h_keys, int* h_idx, u64* ext_keys = nullptr, float* h_dist = nullptr)
 {
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard guard;
@@ -447,7 +447,7 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
     ST_TRY(buf_reserve(&c->r, rbytes));
     ST_TRY(buf_reserve(&c->index, ibytes));
     ST_TRY(buf_reserve(&c->keys, (size_t)m * sizeof(u64)));
-    ST_TRY(buf_reserve(&c->idx, (size_t)m * sizeof(int)));
+    ST_TRY(buf_reserve(&c->idx, (size_t)m * sizeof(int) * (h_dist ? 2 : 1)));
     float* d_q = (float*)c->q.p;
     float* d_r = (float*)c->r.p;
     float* d_index = (float*)c->index.p;
@@ -501,8 +501,10 @@ static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, con
         CU_TRY(cudaMemcpyAsync(h_keys, d_keys, (size_t)m * sizeof(u64), cudaMemcpyDeviceToHost, c->compute));
     }
     if (h_idx) {
-        CU_TRY(launch_keys_unpack(d_keys, m, d_idx, nullptr, c->compute));
+        float* d_dist = h_dist ? (float*)(d_idx + m) : nullptr;  // second half of the idx buffer
+        CU_TRY(launch_keys_unpack(d_keys, m, d_idx, d_dist, c->compute));
         CU_TRY(cudaMemcpyAsync(h_idx, d_idx, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+        if (h_dist) CU_TRY(cudaMemcpyAsync(h_dist, d_dist, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
     }
     CU_TRY(cudaStreamSynchronize(c->compute));
     CU_TRY(cudaStreamSynchronize(c->copy));
@@ -659,6 +661,17 @@ int nns_b200_search_host(int k, int m, int n, const float* s_points, const float
     DeviceCtx* c;
     ST_TRY(ctx_get(-1, &c));
     return search_host_on(c, k, m, n, s_points, r_points, 0, nullptr, results);
+}
+
+int nns_b200_search_host_dist(int k, int m, int n, const float* s_points, const float* r_points, int* results,
+                              float* distances)
+{
+    ST_TRY(check_host_args(k, m, n, s_points, r_points, results));
+    if (m > 0 && !distances) return fail(NNS_B200_ERR_INVALID, "NULL array");
+    if (m == 0) return NNS_B200_OK;
+    DeviceCtx* c;
+    ST_TRY(ctx_get(-1, &c));
+    return search_host_on(c, k, m, n, s_points, r_points, 0, nullptr, results, nullptr, distances);
 }
 
 int nns_b200_search_multi(int k, int m, int n, const float* s_points, const float* r_points, int* results,

@@ -62,6 +62,7 @@ lib.nns_b200_shutdown.argtypes = []
 lib.nns_b200_cudaCall.argtypes = [c_int, c_int, c_int, _fp, _fp, POINTER(POINTER(c_int))]
 lib.nns_b200_cudaCall.restype = None
 lib.nns_b200_search_host.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+lib.nns_b200_search_host_dist.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
 lib.nns_b200_search_multi.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int]
 lib.nns_b200_index_floats.argtypes = [c_int, c_int]
 lib.nns_b200_index_floats.restype = c_size_t
@@ -112,6 +113,16 @@ def search_host(k: int, m: int, n: int, s_points, r_points, out: np.ndarray | No
     _check(lib.nns_b200_search_host(k, m, n, sp, rp, out.ctypes.data))
     del keep
     return out
+
+
+def search_host_dist(k: int, m: int, n: int, s_points, r_points):
+    """nns_b200_search_host_dist: (indices, FP32 squared distances) for host arrays."""
+    s = _host_f32(s_points, m, k)
+    r = _host_f32(r_points, n, k)
+    idx = np.empty(m, dtype=np.int32)
+    dist = np.empty(m, dtype=np.float32)
+    _check(lib.nns_b200_search_host_dist(k, m, n, s.ctypes.data, r.ctypes.data, idx.ctypes.data, dist.ctypes.data))
+    return idx, dist
 
 
 def search_multi(k: int, m: int, n: int, s_points, r_points, num_gpus: int = 0, shard_mode: int = 0) -> np.ndarray:

@@ -90,6 +90,7 @@ def test_argument_validation_needs_no_gpu(nns):
     assert b"NULL" in nns.lib.nns_b200_last_error()
     assert nns.lib.nns_b200_search_host(3, 0, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data) == nns.OK  # nothing to do
     assert nns.lib.nns_b200_search_multi(3, 4, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data, 1, 7) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_search_host_dist(3, 4, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data, None) == nns.ERR_INVALID
     with pytest.raises(nns.NnsError):
         nns.plan(0, 1, 1)
 

@@ -250,6 +250,25 @@ def test_host_ingest_chunking_and_search_multi(nns, oracle):
         assert np.array_equal(g2, g)
 
 
+@pytest.mark.parametrize("k,m,n", [(3, 700, 30000), (16, 300, 9000), (128, 512, 8192), (200, 9, 3000), (3, 4, 0)])
+def test_search_host_dist_returns_the_fp32_distance_of_the_reported_neighbour(nns, oracle, k, m, n):
+    """The distances-out extension (the 1-NN part): indices as nns_b200_search_host,
+    and the FP32 distance of that neighbour accumulated like the engine does (ascending dimensions,
+    FMA) -- equal to an FP64 evaluation to FP32 round-off; +INF when there is no reference."""
+    s, r = make_case("uniform", k, m, max(n, 1), 5)
+    r = r[:n]
+    idx, dist = nns.search_host_dist(k, m, n, s, r)
+    assert np.array_equal(idx, nns.search_host(k, m, n, s, r))
+    if n == 0:
+        assert np.all(idx == 0) and np.all(np.isinf(dist))
+        return
+    d64 = ((s.astype(np.float64) - r[idx].astype(np.float64)) ** 2).sum(axis=1)
+    assert np.allclose(dist, d64, rtol=(k + 4) * 2.0 ** -23, atol=0.0)
+    v = oracle.v0(k, m, n, s, r)
+    rep = oracle.check_tie_rule(k, m, n, s, r, idx, v, REL_TOL)
+    assert rep["violations"] == 0, rep
+
+
 def test_search_device_one_shot(nns, oracle, torch_mod):
     k, m, n = 5, 700, 9000
     s, r = make_case("uniform", k, m, n, 12)
