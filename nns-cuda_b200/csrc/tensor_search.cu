@@ -54,8 +54,11 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #ifndef NNS_T_TEAMS
 #define NNS_T_TEAMS 2       // epilogue teams of 8 warps; team i owns TMEM buffer i and reduces the tiles t % 2 == i
 #endif
+#ifndef NNS_T_SUB
+#define NNS_T_SUB 2         // accumulator units per reference tile for the short contractions (KB = 0): 1 or 2
+#endif
 #ifndef NNS_T_LD64
-#define NNS_T_LD64 0        // 1: the epilogue reads 64 TMEM columns per load (two round trips per tile instead of four)
+#define NNS_T_LD64 (-1)     // TMEM columns per epilogue load: 0 = 32, 1 = 64, -1 = 64 for 64-column units (SUB = 2) else 32
 #endif
 #ifndef NNS_T_SPIN
 #define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
@@ -77,7 +80,6 @@ constexpr int T_THREADS = 32 * (T_SERVICE_WARPS + T_TEAMS * T_TEAM_WARPS);
 // one CTA per SM: the whole register file.  Registers are per scheduler (16384 each), and the
 // busiest one hosts ceil(warps / 4) warps
 constexpr int T_MAX_REGS = (16384 / (32 * ((T_THREADS / 32 + 3) / 4))) & ~7;
-constexpr int T_CPW = T_BN / 32;                       // 32-column chunks per epilogue warp per tile
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM helpers
@@ -160,8 +162,6 @@ __device__ __forceinline__ u64 umma_desc_interleave(uint32_t smem_addr, uint32_t
     d |= (u64)1 << 46;                    // descriptor version
     return d;                             // layout type 0 = no swizzle
 }
-// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128
-constexpr uint32_t T_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // order-preserving float <-> uint (for atomicMin on possibly negative scores)
 __device__ __forceinline__ unsigned f2ord(float f)
@@ -260,7 +260,7 @@ __device__ __forceinline__ __nv_bfloat16 bf16_part(float x, int part)
 }
 
 // ---------------------------------------------------------------------------------------------
-// reference-side preparation (part of index_build for 32 < k <= 128)
+// reference-side preparation (part of index_build for k <= 128)
 // ---------------------------------------------------------------------------------------------
 // section header (floats): [0..127] centre, [128] max |r'|^2 (bits), [129] flags (bit 0: unusable)
 __global__ void tensor_colsum_kernel(const float* __restrict__ aos, const int n, const int k, float* __restrict__ sums)
@@ -437,7 +437,14 @@ __device__ __forceinline__ void cand_emit(const CandBuf& cb, unsigned* s_count, 
 
 // G = reference tiles per TMA stage: short contractions (KB = 0) move 4 KiB / 8 KiB tiles, and one
 // mbarrier round trip per tile on the MMA issuer's critical path costs more than the MMAs themselves
-template <int KB, int KS, int T_STAGES, int G>
+// SUB = accumulator units per reference tile: the 128-reference tile is issued as SUB MMAs of
+// N = 128 / SUB columns into 2 * SUB TMEM buffers.  An epilogue team owns the buffers of its parity,
+// so with SUB = 2 it reduces one of its two buffers while the other is being refilled (with one
+// buffer per team the team idles for the refill: 23 % of its time in the ncu source view of the
+// SUB = 1 build at k = 3).  Only for KB = 0: an N = 64 MMA re-reads the A operand twice as often, and
+// at M = 128 the shared-memory operand fetch already runs at its 128 B/clk limit when the tensor
+// pipe is the bound (k >= 10).
+template <int KB, int KS, int T_STAGES, int G, int SUB>
 __global__ void __maxnreg__(T_MAX_REGS)
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
@@ -448,6 +455,11 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     constexpr uint32_t A_BYTES = (uint32_t)image_bytes(T_BM, KB, KS);  // 72 KiB at KB = 2, KS = 1
     constexpr uint32_t B_BYTES = (uint32_t)image_bytes(T_BN, KB, KS);  // 36 KiB at KB = 2, KS = 1
     constexpr uint32_t STAGE_BYTES = G * B_BYTES;
+    constexpr int NBUF = 2 * SUB;              // TMEM accumulator buffers
+    constexpr int SN = T_BN / SUB;             // references (TMEM columns) per accumulator unit
+    constexpr int CPU = SN / 32;               // 32-column chunks per unit
+    // instruction descriptor: D = F32, A = B = BF16, both K-major, N = SN, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_smem = smem;
     unsigned char* b_smem = smem + A_BYTES;
@@ -456,7 +468,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     unsigned* s_cand_count = tmem_slot + 1;
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_full = bar0, b_empty = bar0 + 8 * T_STAGES;
-    const uint32_t acc_full = bar0 + 8 * 2 * T_STAGES, acc_empty = acc_full + 16, a_full = acc_empty + 16;
+    const uint32_t acc_full = bar0 + 8 * 2 * T_STAGES, acc_empty = acc_full + 8 * NBUF, a_full = acc_empty + 8 * NBUF;
 
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     const int t0 = (int)blockIdx.y * tiles_per_split;
@@ -471,7 +483,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_TEAM_WARPS); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_TEAM_WARPS); }
         mbar_init(a_full, 1);
         mbar_fence_init();
         *s_cand_count = 0;
@@ -535,41 +547,48 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             int s = 0, j = 0;
             uint32_t ph = 0;
             uint32_t boff16 = 0;  // (byte offset of the current B tile inside the ring) >> 4: added to the descriptors' start-address field
-            auto issue_tile = [&](const int t, const int buf) {
-                mbar_wait_mma(acc_empty + 8 * buf, (uint32_t)(((t >> 1) & 1) ^ 1));  // its team drained this buffer
-                if (j == 0) mbar_wait_mma(b_full + 8 * s, ph);                      // TMA landed this stage
+            // one accumulator unit: references [sub * SN, sub * SN + SN) of the current tile into buffer `buf`
+            auto issue_unit = [&](const int u, const int buf, const int sub) {
+                mbar_wait_mma(acc_empty + 8 * buf, (uint32_t)(((u / NBUF) & 1) ^ 1));  // its team drained this buffer
+                if (j == 0 && sub == 0) mbar_wait_mma(b_full + 8 * s, ph);               // TMA landed this stage
                 tc_fence_after();
+                // rows sub * SN .. of the B tile: SN rows of 128 B in a swizzled block, of 16 B in an interleaved chunk
+                const uint32_t sw16 = boff16 + (uint32_t)(sub * SN * 128 >> 4), il16 = boff16 + (uint32_t)(sub * SN * 16 >> 4);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const u64 bdesc = ((u64)bdesc_sw_hi << 32) | (u64)(bdesc_sw_lo[kb][ks] + boff16);
+                        const u64 bdesc = ((u64)bdesc_sw_hi << 32) | (u64)(bdesc_sw_lo[kb][ks] + sw16);
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
-                            if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc_sw[kb][ks][h], bdesc, T_IDESC, (uint32_t)((kb | ks) != 0));
+                            if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_sw[kb][ks][h], bdesc, IDESC, (uint32_t)((kb | ks) != 0));
                     }
 #pragma unroll
                 for (int x = 0; x < KS; ++x) {  // interleaved steps (the last columns carry |r'|^2)
-                    const u64 bdesc = ((u64)bdesc_il_hi << 32) | (u64)(bdesc_il_lo[x] + boff16);
+                    const u64 bdesc = ((u64)bdesc_il_hi << 32) | (u64)(bdesc_il_lo[x] + il16);
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
-                        if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * T_BN), adesc_il[x][h], bdesc, T_IDESC, (uint32_t)((KB | x) != 0));
+                        if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_il[x][h], bdesc, IDESC, (uint32_t)((KB | x) != 0));
                 }
                 tc_commit(acc_full + 8 * buf);   // accumulator complete
-                T_TRACE(3, t);
-                if (j == G - 1 || t == nt - 1) {
-                    tc_commit(b_empty + 8 * s);  // stage free once the MMAs of its tiles have read it
-                    j = 0;
-                    if (++s == T_STAGES) { s = 0; ph ^= 1u; }
-                    boff16 = (uint32_t)s * (STAGE_BYTES >> 4);
-                } else {
-                    ++j;
-                    boff16 += B_BYTES >> 4;
+                T_TRACE(3, u);
+                if (sub == SUB - 1) {            // last unit of the tile
+                    if (j == G - 1 || u == nt * SUB - 1) {
+                        tc_commit(b_empty + 8 * s);  // stage free once the MMAs of its tiles have read it
+                        j = 0;
+                        if (++s == T_STAGES) { s = 0; ph ^= 1u; }
+                        boff16 = (uint32_t)s * (STAGE_BYTES >> 4);
+                    } else {
+                        ++j;
+                        boff16 += B_BYTES >> 4;
+                    }
                 }
             };
-            for (int t = 0; t < nt; t += 2) {
-                issue_tile(t, 0);
-                if (t + 1 < nt) issue_tile(t + 1, 1);
+            // unrolled over the TMEM buffers: buffer and barrier addresses are immediates
+            for (int u = 0; u < nt * SUB; u += NBUF) {
+#pragma unroll
+                for (int i = 0; i < NBUF; ++i)
+                    if (u + i < nt * SUB) issue_unit(u + i, i, i % SUB);
             }
         }
     } else {
@@ -588,22 +607,21 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         // other CTAs (reference splits, earlier waves) may already have lowered this query's minimum
         float run_min = (q < m) ? ord2f(approx_min[q]) : inf_f();
         float thresh = run_min + my_band;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * T_BN);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * SN);
         // One TMEM chunk in flight per warp: with four epilogue warps per scheduler the load latency
         // of one warp is covered by the reductions of the other three.  (A register double buffer
         // measured no faster at k = 3 and slower at k = 128, where the box runs at its power cap.)
-#if NNS_T_LD64
-        uint32_t v[64];
-#else
-        uint32_t v[1][32];
-#endif
+        // a 64-column unit (SUB = 2) is read with ONE 64-column load; 128-column units 32 columns at a time
+        constexpr bool LD64 = NNS_T_LD64 < 0 ? (CPU == 2) : (NNS_T_LD64 != 0);
+        uint32_t v[LD64 ? 64 : 32];
 #if NNS_T_EXPERIMENT >= 2
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[0][i] = 0x7f800000u;
+        for (int i = 0; i < (LD64 ? 64 : 32); ++i) v[i] = 0x7f800000u;
 #define tmem_ld32(a, b) ((void)0)
+#define tmem_ld64(a, b) ((void)0)
 #endif
         // reduce one 32-column chunk, emit it as a candidate when it is within the band
-        auto reduce_chunk = [&](const uint32_t (&cur)[32], const int t, const int c) {
+        auto reduce_chunk = [&](const uint32_t (&cur)[32], const int unit32) {
 #if NNS_T_EXPERIMENT >= 1
             const float cm = fminf(__uint_as_float(cur[0]), __uint_as_float(cur[31]));
 #else
@@ -628,7 +646,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             // candidates have 32-reference granularity (one TMEM chunk): 4x less to re-score than a tile
             if (NNS_T_EXPERIMENT < 2 && cm <= thresh) {
                 TensorCand cnd;
-                cnd.q = (int)q; cnd.unit = (t0 + t) * (T_BN / 32) + c; cnd.smin = cm;
+                cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
                 cand_emit(cb, s_cand_count, cta, cnd);
                 if (cm < run_min) {
                     run_min = cm;
@@ -637,47 +655,52 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 }
             }
         };
-        for (int t = (T_TEAMS == 2 ? team : 0); t < nt; t += T_TEAMS) {
-            const int buf = t & 1;
-            const uint32_t taddr = lane_base + (uint32_t)(buf * 2 * T_BN);
-            mbar_wait_hot(acc_full + 8 * buf, (uint32_t)((t >> 1) & 1));
-            if (lane == 0) T_TRACE(4 + e, t);
+        // team i reduces the units u = i, i + 2, ...: buffer u % NBUF (its own parity), 32-reference
+        // candidate units t0 * 4 + u * CPU + c
+        for (int u = (T_TEAMS == 2 ? team : 0); u < nt * SUB; u += T_TEAMS) {
+            const int buf = u % NBUF;
+            const uint32_t taddr = lane_base + (uint32_t)(buf * 2 * SN);
+            const int unit0 = t0 * (T_BN / 32) + u * CPU;
+            mbar_wait_hot(acc_full + 8 * buf, (uint32_t)((u / NBUF) & 1));
+            if (lane == 0) T_TRACE(4 + e, u);
             tc_fence_after();
-            // The chunk loop is deliberately NOT unrolled: unrolled, ptxas hoists all four loads to the
-            // top of the tile and spills the loop invariants to make room for 128 destination registers.
-#if NNS_T_LD64
+            if constexpr (LD64) {
+                static_assert(!LD64 || CPU % 2 == 0, "64-column loads need an even number of chunks per unit");
 #pragma unroll 1
-            for (int c = 0; c < T_CPW; c += 2) {
-                tmem_ld64(taddr + c * 32, v);
-                tmem_ld_wait();
-                if (c + 2 == T_CPW) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
-                    if (lane == 0) T_TRACE(4 + 16 + e, t);
+                for (int c = 0; c < CPU; c += 2) {
+                    tmem_ld64(taddr + c * 32, *reinterpret_cast<uint32_t(*)[64]>(&v[0]));
+                    tmem_ld_wait();
+                    if (c + 2 == CPU) {
+                        // every TMEM read of this warp for this unit has completed: hand the accumulator
+                        // back to the MMA issuer before reducing
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                        if (lane == 0) T_TRACE(4 + 16 + e, u);
+                    }
+                    reduce_chunk(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), unit0 + c);
+                    reduce_chunk(*reinterpret_cast<const uint32_t(*)[32]>(&v[LD64 ? 32 : 0]), unit0 + c + 1);
                 }
-                reduce_chunk(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), t, c);
-                reduce_chunk(*reinterpret_cast<const uint32_t(*)[32]>(&v[32]), t, c + 1);
-            }
-#else
+            } else {
+                // The chunk loop is deliberately NOT unrolled: unrolled, ptxas hoists all loads to the top
+                // of the unit and spills the loop invariants to make room for the destination registers.
 #pragma unroll 1
-            for (int c = 0; c < T_CPW; ++c) {
-                tmem_ld32(taddr + c * 32, v[0]);
-                tmem_ld_wait();
-                if (c + 1 == T_CPW) {
-                    // every TMEM read of this warp for tile t has completed: hand the accumulator back
-                    // to the MMA issuer before reducing the last chunk
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
-                    if (lane == 0) T_TRACE(4 + 16 + e, t);
+                for (int c = 0; c < CPU; ++c) {
+                    tmem_ld32(taddr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                    tmem_ld_wait();
+                    if (c + 1 == CPU) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                        if (lane == 0) T_TRACE(4 + 16 + e, u);
+                    }
+                    reduce_chunk(*reinterpret_cast<const uint32_t(*)[32]>(&v[0]), unit0 + c);
                 }
-                reduce_chunk(v[0], t, c);
             }
-#endif
         }
 #if NNS_T_EXPERIMENT >= 2
 #undef tmem_ld32
+#undef tmem_ld64
 #endif
     }
     tc_fence_before();
@@ -804,14 +827,14 @@ static size_t tensor_smem_bytes(const TensorGeom& g)
            (2 * T_MAX_STAGES + 8) * 8 + 16;
 }
 
-template <int KB, int KS, int STAGES, int G>
+template <int KB, int KS, int STAGES, int G, int SUB>
 static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
                                         const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
                                         const CandBuf& cb)
 {
-    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_screen_kernel<KB, KS, STAGES, G><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb);
+    tensor_screen_kernel<KB, KS, STAGES, G, SUB><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb);
     return cudaGetLastError();
 }
 
@@ -900,14 +923,14 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         // CTA is resident per SM even at KP = 64
         const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
         dim3 grid((unsigned)strips, (unsigned)splits);
-#define NNS_SCREEN(KB_, KS_, ST_, G_) \
-    tensor_screen_launch<KB_, KS_, ST_, G_>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cb)
-        if (g.KB == 0 && g.KS == 1) e = NNS_SCREEN(0, 1, 6, 4);
-        else if (g.KB == 0) e = NNS_SCREEN(0, 2, 6, 2);
-        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1);
-        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 6, 1);
-        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 4, 1);
-        else e = NNS_SCREEN(2, 1, 4, 1);
+#define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_) \
+    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cb)
+        if (g.KB == 0 && g.KS == 1) e = NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB);
+        else if (g.KB == 0) e = NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB);
+        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1, 1);
+        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 6, 1, 1);
+        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 4, 1, 1);
+        else e = NNS_SCREEN(2, 1, 4, 1, 1);
 #undef NNS_SCREEN
     }
     if (e == cudaSuccess) {
@@ -930,8 +953,5 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;
 }
-
-// 1 if the index section says the tensor path must not be used (non-finite / huge inputs)
-__global__ void tensor_flag_kernel(const float* hdr, int* out) { *out = (int)(reinterpret_cast<const unsigned*>(hdr)[129] & 1u); }
 
 }  // namespace nns
