@@ -74,6 +74,10 @@ extern "C" int nns_b200_debug_trace(long long* out) { return (int)cudaMemcpyFrom
 #define T_TRACE(ev, t) ((void)0)
 #endif
 constexpr int T_TEAMS = NNS_T_TEAMS;
+// Every accumulator mbarrier must have ONE waiting team, in phase order: a waiter that is more than one
+// phase ahead of an mbarrier misreads its parity.  Two teams and 2 or 4 buffers satisfy that (buffer
+// parity = team); three teams over 2 or 4 buffers do not (deadlocked on B200).
+static_assert(T_TEAMS == 1 || T_TEAMS == 2, "epilogue teams: 1 or 2");
 constexpr int T_TEAM_WARPS = 8;                        // one warp per (TMEM lane quarter, accumulator half)
 constexpr int T_SERVICE_WARPS = 2;                     // warp 0 = TMA producer, warp 1 = MMA issuer
 constexpr int T_THREADS = 32 * (T_SERVICE_WARPS + T_TEAMS * T_TEAM_WARPS);
