@@ -23,13 +23,15 @@
 //   warp 0   producer: 1-D bulk copies (TMA) of the pre-swizzled BF16 images: the strip's A tile
 //            once, then the B tiles through an mbarrier ring (G tiles per stage: 4 KiB tiles are
 //            moved four at a time so that the ring costs one barrier round trip per 16 KiB)
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.kind::f16 M=128 N=128 K=16, two
-//            accumulator halves (query rows 0-127 / 128-255) x two buffers = all 512 TMEM columns;
-//            tcgen05.commit publishes the accumulator and releases the B stage
-//   warps 2-17 epilogue, two teams of 8 warps: team i owns TMEM buffer i and reduces the tiles
-//            t % 2 == i; thread = query row; tcgen05.ld 32 columns at a time, FMNMX3 tree, candidate
-//            test.  |r'|^2 is folded into the contraction (A carries 1,1,1; B carries |r'|^2 split
-//            into three BF16 terms), so the epilogue touches neither shared memory nor the FP32 pipe.
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma.kind::f16 M=128 N=128 K=16, two
+//            accumulator halves (query rows 0-127 / 128-255) x two buffers = all 512 TMEM columns
+//            (k <= 9: N=64 units, two per tile, in four buffers); tcgen05.commit publishes the
+//            accumulator and releases the B stage
+//   warps 2-17 epilogue, two teams of 8 warps: team i owns the TMEM buffers of parity i and reduces
+//            the accumulator units u % 2 == i; thread = query row; tcgen05.ld 32 (64) columns at a
+//            time, FMNMX3 tree, candidate test.  |r'|^2 is folded into the contraction (A carries
+//            1,1,1; B carries |r'|^2 split into three BF16 terms), so the epilogue touches neither
+//            shared memory nor the FP32 pipe.
 // Why two teams: for short contractions the tile pipeline is a chain of latencies -- commit ->
 // epilogue wake-up -> four TMEM-load round trips -> release -> issuer wake-up -> MMA issue -> MMA --
 // of ~1300 clk per TMEM buffer, of which only ~150 clk per warp are FMNMX3 issue slots
