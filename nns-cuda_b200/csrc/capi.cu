@@ -566,6 +566,10 @@ int nns_b200_shutdown(void)
             c->events.clear();
             cudaStreamDestroy(c->compute);
             cudaStreamDestroy(c->copy);
+            // hand the stream-ordered scratch kept in the device's default pool back to the driver
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+            cudaGetLastError();
             c->ready = false;
             c->occ_cache.clear();
         }
