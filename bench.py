@@ -43,6 +43,9 @@ WORKLOADS = {
     "c3": (16, 262144, 16777216, "uniform", "reference"),
     "c4": (128, 1048576, 1048576, "uniform", "query"),
     "c5": (3, 16777216, 16777216, "clustered", "query"),
+    # not a BASELINE config: the reference's m = 1 shapes (main.cu:39-42) scaled up -- the low-arithmetic-intensity
+    # case the north-star wants reported as achieved HBM GB/s (reference-parallel kernel, 4(k+1)n bytes per call)
+    "m1": (16, 1, 16777216, "uniform", "query"),
 }
 SM_COUNT = 148
 FP32_LANES_PER_SM = 128
@@ -207,7 +210,7 @@ def run_reference_arm(args):
 def workload_config(name, n_gpus, sharding, l2):
     k, m, n, kind, _ = WORKLOADS[name]
     return {"workload": f"{name.upper()}: k={k}, m={m} queries, n={n} {kind} fp32 reference points "
-                        f"(BASELINE.json configs[{list(WORKLOADS).index(name)}])",
+                        + (f"(BASELINE.json configs[{list(WORKLOADS).index(name)}])" if name != "m1" else "(the reference's m = 1 shape, main.cu:39-42, at 16.7 M references)"),
             "k": k, "m": m, "n": n, "distribution": kind, "sharding": sharding, "l2": l2,
             "queries_per_gpu": m if sharding.startswith("query") else m, "n_gpus": n_gpus}
 

@@ -183,6 +183,7 @@ static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn oc
         if (s > max_s) s = max_s;
         if (s > 65535) s = 65535;
         p->bps = ceil_div(nblocks, s) > 0 ? ceil_div(nblocks, s) : 1;
+        p->bps = ceil_div(p->bps, WIDE_THREADS / 32) * (WIDE_THREADS / 32);  // one block per warp at a time: whole rounds
         p->splits = ceil_div(nblocks, p->bps) > 0 ? ceil_div(nblocks, p->bps) : 1;
         p->smem = (int)smem;
         return NNS_B200_OK;

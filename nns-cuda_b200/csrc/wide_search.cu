@@ -3,11 +3,13 @@
 // queries (the reference's m = 1 benchmark shapes, main.cu:39-42, which are HBM-bound).
 //
 // A CTA takes WIDE_QT queries (coordinates broadcast from shared memory) and a range of
-// reference blocks; each thread owns one lane of a 128-point block, reads its coordinates with
-// coalesced loads from the tiled-SoA index, keeps a running (dist, idx) per query (ascending j,
-// strict '<' => first minimum, as V0 core.cu:44), and the CTA merges through the packed key:
-// warp shuffle min -> shared memory -> one atomicMin per query.  Same result semantics and the
-// same FP32 operation order (ascending t, FMA or V0 rounding) as the low-k kernel.
+// reference blocks; each WARP owns one 128-point block at a time and each lane four consecutive
+// points of it, read with one 16-byte load per dimension (a warp reads a whole 512-byte row of the
+// tiled-SoA index per instruction: the m = 1 shapes are HBM-bound and need the bytes in flight).
+// A thread keeps a running (dist, idx) per query over its points in ascending index order (strict
+// '<' => first minimum, as V0 core.cu:44), and the CTA merges through the packed key: warp shuffle
+// min -> shared memory -> one atomicMin per query.  Same result semantics and the same FP32 operation
+// order (ascending t, FMA or V0 rounding) as the low-k kernel.
 // Replaces the structure of v7::cudaCallKernel + host merge (core.cu:589-633, 669-696).
 #include "nns_internal.h"
 
@@ -34,44 +36,44 @@ wide_search_kernel(const float* __restrict__ queries, const int m, const int k,
 
     const int b0 = (int)blockIdx.y * blocks_per_split;
     const int b1 = min(nblocks, b0 + blocks_per_split);
-    const int half = (int)(threadIdx.x >> 7);  // WIDE_THREADS / LB = 2 blocks in flight
-    const int l = (int)(threadIdx.x & (LB - 1));
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
 
     float best[WIDE_QT];
     int bidx[WIDE_QT];
 #pragma unroll
     for (int i = 0; i < WIDE_QT; ++i) { best[i] = inf_f(); bidx[i] = 0; }
 
-    for (int b = b0 + half; b < b1; b += WIDE_THREADS / LB) {
-        const float* blk = blocks + (size_t)b * (k + 1) * LB + l;  // rows 0..k-1 (row k = |r|^2 is not used here)
-        float acc[WIDE_QT];
+    for (int b = b0 + warp; b < b1; b += WIDE_THREADS / 32) {
+        // rows 0..k-1 of block b (row k = |r|^2 is not used here); lane = points 4*lane .. 4*lane+3
+        const float4* blk = reinterpret_cast<const float4*>(blocks + (size_t)b * (k + 1) * LB) + lane;
+        float acc[4][WIDE_QT];
 #pragma unroll
-        for (int i = 0; i < WIDE_QT; ++i) acc[i] = 0.0f;
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int i = 0; i < WIDE_QT; ++i) acc[e][i] = 0.0f;
 #pragma unroll 4
         for (int t = 0; t < k; ++t) {
-            const float r = __ldg(blk + (size_t)t * LB);
+            const float4 r4 = __ldg(blk + (size_t)t * (LB / 4));
             const float4 q4 = *reinterpret_cast<const float4*>(qs + t * WIDE_QT);
-            const float d0 = q4.x - r, d1 = q4.y - r, d2 = q4.z - r, d3 = q4.w - r;
-            if (EXACT) {
-                acc[0] = __fadd_rn(acc[0], __fmul_rn(d0, d0));
-                acc[1] = __fadd_rn(acc[1], __fmul_rn(d1, d1));
-                acc[2] = __fadd_rn(acc[2], __fmul_rn(d2, d2));
-                acc[3] = __fadd_rn(acc[3], __fmul_rn(d3, d3));
-            } else {
-                acc[0] = __fmaf_rn(d0, d0, acc[0]);
-                acc[1] = __fmaf_rn(d1, d1, acc[1]);
-                acc[2] = __fmaf_rn(d2, d2, acc[2]);
-                acc[3] = __fmaf_rn(d3, d3, acc[3]);
-            }
-        }
-        const int j = index_base + b * LB + l;
+            const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+            const float q[WIDE_QT] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-        for (int i = 0; i < WIDE_QT; ++i) {
-            if (acc[i] < best[i]) { best[i] = acc[i]; bidx[i] = j; }
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int i = 0; i < WIDE_QT; ++i) {
+                    const float d = q[i] - r[e];
+                    acc[e][i] = EXACT ? __fadd_rn(acc[e][i], __fmul_rn(d, d)) : __fmaf_rn(d, d, acc[e][i]);
+                }
         }
+        const int j = index_base + b * LB + 4 * lane;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)  // ascending index: the first minimum wins
+#pragma unroll
+            for (int i = 0; i < WIDE_QT; ++i) {
+                if (acc[e][i] < best[i]) { best[i] = acc[e][i]; bidx[i] = j + e; }
+            }
     }
 
-    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
 #pragma unroll
     for (int i = 0; i < WIDE_QT; ++i) {
         u64 key = pack_key(best[i], bidx[i]);
