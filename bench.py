@@ -7,7 +7,10 @@
 A "step" is one pass of the hot path over one batch: keys_init + fused distance/argmin search of
 m queries against the HBM-resident tiled-SoA index of n references + key unpack, called through
 the C ABI (libnns_b200.so).  Metric = pair-distance evaluations per second (m*n / t), whole job.
-Default workload = BASELINE.json configs[1] ("C2": k=3, m=65,536, n=4,194,304 uniform fp32).
+Default workload = BASELINE.json configs[1] ("C2": k=3, m=65,536, n=4,194,304 uniform fp32); the
+library's planner picks the kernel (C2: the split-precision tcgen05 screen + exact FP32 re-score),
+`--flags` forces another one (2 = FP32 screened kernel, 16 = V0's formulation on the FP32 pipe).
+`roofline` describes the kernel that ran, against the resource that binds it.
 With N > 1 the queries are sharded (each rank searches its own m queries against the replicated
 reference set: weak scaling, no data-path collective); `--shard reference` splits the references
 instead and merges the packed (dist, idx) keys with an NCCL MIN all-reduce (BASELINE config C3).
