@@ -122,3 +122,41 @@ def test_screen_error_stays_inside_the_band(k, case):
     # the bound must also be worth something: on the unit cube E is a small fraction of the spread of distances
     if case == "uniform":
         assert (E.astype(np.float64) < 0.05 * d.max(axis=1)).all()
+
+
+@pytest.mark.parametrize("k,case", [(3, "uniform"), (3, "clustered"), (16, "uniform"), (16, "mixed"), (128, "uniform"), (64, "offset1000")])
+def test_screen_and_rescore_logic_returns_v0(k, case):
+    """The screen's control logic on top of the emulated scores, as the kernels run it: per query a
+    running minimum over 32-reference units in index order, a unit is recorded when its minimum is
+    within the band 2E of the running minimum, recorded units within 2E of the FINAL minimum are
+    re-scored exactly (V0's FP32 distances), and the smallest packed (distance, index) key wins.
+    Whatever the unit order and the rounding of the scores, the answer must be V0's: first minimum
+    of the FP32 distances.  (Grid-snapped clustered data: many exact ties.)"""
+    m, n = 40, 2048
+    if case == "clustered":
+        s, r = make_case("clustered", k, m, n, 3)
+    else:
+        s, r = make_case("uniform", k, m, n, 3)
+        if case == "offset1000":
+            s, r = (s.astype(np.float64) + 1000.0).astype(F32), (r.astype(np.float64) + 1000.0).astype(F32)
+        if case == "mixed":
+            r = r.copy()
+            r[::7] *= F32(50.0)
+    acc, E, _ = screen_scores(k, s, r)
+    d = v0_distances(s, r)
+    v0 = d.argmin(axis=1)  # numpy argmin = first minimum = V0's strict '>' update (core.cu:44)
+    band = (F32(2.0) * E).astype(F32)
+    total_candidates = 0
+    for q in range(m):
+        run_min, cand = F32(np.inf), []
+        for u in range(n // 32):
+            cm = acc[q, 32 * u:32 * u + 32].min()
+            if cm <= run_min + band[q]:
+                cand.append((u, cm))
+                run_min = min(run_min, cm)
+        live = [u for (u, cm) in cand if cm <= run_min + band[q]]
+        total_candidates += len(live)
+        best = min((d[q, j], j) for u in live for j in range(32 * u, 32 * u + 32))
+        assert best[1] == v0[q], (q, best, v0[q], d[q, v0[q]])
+    if case != "mixed":  # references 50x farther out inflate max |r'| and with it the band: still exact, no longer selective
+        assert total_candidates < m * (n // 32) // 2  # the screen screens
