@@ -482,7 +482,12 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
     // nothing to do, or an earlier CTA ran out of candidate space (dense near-ties: the FP32 kernel
     // launched after the re-score redoes the whole search, so the rest of this pass would be wasted)
-    if (nt <= 0 || *reinterpret_cast<volatile const unsigned*>(cb.counters + 1) != 0u) {
+    // (one thread reads the flag for the whole CTA: it can flip between two threads' reads, and a CTA
+    // of which only some threads leave would hang at the first barrier)
+    __shared__ unsigned s_abort;
+    if (threadIdx.x == 0) s_abort = *reinterpret_cast<volatile const unsigned*>(cb.counters + 1);
+    __syncthreads();
+    if (nt <= 0 || s_abort != 0u) {
         if (threadIdx.x == 0) cb.cta_count[cta] = 0;
         return;
     }
