@@ -652,7 +652,11 @@ int nns_b200_search_device(int k, int m, int n, const float* d_queries, const fl
     std::lock_guard<std::mutex> lk(c->mu);
     CU_TRY(launch_keys_init(d_keys, m, st));
     CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_index + INDEX_HEADER_FLOATS, true, st));
-    CU_TRY(tensor_index_build(k, n, d_refs_aos, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * index_block_floats(k), st));
+    // the tensor section only when this search is planned onto the tcgen05 path (as in search_host_on)
+    Plan whole{};
+    if (n > 0) ST_TRY(make_plan(k, m, n, flags, c->num_sms, nullptr, nullptr, &whole));
+    if (whole.path == 2)
+        CU_TRY(tensor_index_build(k, n, d_refs_aos, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * index_block_floats(k), st));
     g_launches.fetch_add(n > 0 ? 3 : 2, std::memory_order_relaxed);  // + the unpack below
     ST_TRY(search_keys_on(c, k, m, n, d_queries, d_index, d_index + INDEX_HEADER_FLOATS, 0, d_keys, flags, st));
     CU_TRY(launch_keys_unpack(d_keys, m, d_idx, nullptr, st));
