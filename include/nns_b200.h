@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NNS_B200_VERSION 100
+#define NNS_B200_VERSION 200
 
 /* status codes of the int-returning entry points */
 #define NNS_B200_OK 0
@@ -87,6 +87,19 @@ int nns_b200_search_host_dist(int k, int m, int n, const float *s_points, const 
 int nns_b200_search_multi(int k, int m, int n, const float *s_points, const float *r_points,
                           int *results, int num_gpus, int shard_mode);
 
+/* ---- device-resident index handle: build once, query many -----------------------------------
+ * The reference uploads and transposes the reference set inside every call (core.cu:351-370 and its
+ * copies in v4..v9); a handle keeps the tiled-SoA index (and, once a search is planned onto the
+ * tcgen05 path, its BF16 operand images) resident in the HBM of `device` (< 0: the current device).
+ * r_points / s_points are host arrays exactly as in the drop-in symbol (pageable or pinned);
+ * distances may be NULL.  Searches on one handle are serialised; handles are independent. */
+typedef struct nns_b200_index nns_b200_index_t;
+int nns_b200_index_create(int k, int n, const float *r_points, int device, nns_b200_index_t **out);
+int nns_b200_index_search(nns_b200_index_t *index, int m, const float *s_points, int *results,
+                          float *distances);
+int nns_b200_index_size(const nns_b200_index_t *index, int *k, int *n);
+int nns_b200_index_destroy(nns_b200_index_t *index);
+
 /* ---- lifetime ----------------------------------------------------------------------------
  * Replaces the load-time WarmUP static initialiser (core.cu:1900-1933): nothing touches the
  * GPU at load; nns_b200_init(device) creates the per-device state eagerly (device < 0 = the
@@ -95,6 +108,7 @@ int nns_b200_search_multi(int k, int m, int n, const float *s_points, const floa
 int nns_b200_init(int device);
 int nns_b200_shutdown(void);
 int nns_b200_version(void);
+int nns_b200_device_sms(int device); /* SM count of the device (< 0: current); -1 on failure */
 const char *nns_b200_last_error(void); /* thread-local text of the last failure */
 
 /* ---- device-resident building blocks (inputs already in HBM) ------------------------------ */
@@ -105,6 +119,23 @@ size_t nns_b200_index_floats(int k, int n);
 /* AoS float[n][k] (device) -> tiled SoA index (device, nns_b200_index_floats(k,n) floats,
  * 16-byte aligned).  Replaces v4::mat_inv_kernel (core.cu:293-306). */
 int nns_b200_index_build(int k, int n, const float *d_refs_aos, float *d_index, void *stream);
+
+/* An index that several GPUs build together (one process per GPU, e.g. under torch.distributed):
+ * each builds the slice [j0, j0 + cn) of the n_total references -- `part_blocks` blocks starting at block
+ * j0 / 128, of which those past cn points are padding -- straight into its copy of the index, with the
+ * centre of the tcgen05 operand images fixed by the caller (nns_b200_sample_centre on the host array,
+ * so that every slice uses the same one); the slices' byte ranges (nns_b200_index_part_ranges: out6 =
+ * { blocks offset, blocks bytes, image offset, image bytes, index-header word offset, section-header
+ * word offset }, bytes from d_index; the two header words are 4 bytes each, and the section's flag word
+ * lies 64 bytes after its partial-max word) are then exchanged (all-gather over NVLink), and
+ * nns_b200_index_finish folds the per-part maxima.  Replaces v8/v9's "every GPU uploads and transposes
+ * everything it needs" (core.cu:778-818, 982-1022). */
+int nns_b200_sample_centre(int k, int n, const float *r_points, float *centre_out);
+int nns_b200_index_build_part(int k, int n_total, int j0, int cn, int part_blocks,
+                              const float *d_refs_aos_part, float *d_index, const float *centre,
+                              int part, void *stream);
+int nns_b200_index_part_ranges(int k, int n_total, int j0, int part_blocks, int part, size_t *out6);
+int nns_b200_index_finish(int k, int n_total, float *d_index, int parts, void *stream);
 
 /* keys[i] = NNS_B200_KEY_INIT for i < m */
 int nns_b200_keys_init(uint64_t *d_keys, int m, void *stream);

@@ -1,23 +1,16 @@
 // capi.cu -- the C ABI of include/nns_b200.h: planning, per-device state, host-pointer
 // ingest, single-process multi-GPU fan-out.  All compute is in the CUDA kernels of this
 // library; there is no CPU search path anywhere in this file.
-#include "../../include/nns_b200.h"
-
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <mutex>
 #include <string>
-#include <thread>
-#include <tuple>
-#include <vector>
 
-#include "nns_internal.h"
+#include "host_state.h"
 
-using namespace nns;
+namespace nns {
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -27,7 +20,7 @@ static thread_local char g_err_file[128] = "";
 static thread_local int g_err_line = 0;
 static thread_local int g_err_code = 0;
 
-static int fail(int status, const char* fmt, ...)
+int fail(int status, const char* fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -36,7 +29,7 @@ static int fail(int status, const char* fmt, ...)
     return status;
 }
 
-static int fail_cuda(cudaError_t e, const char* file, int line)
+int fail_cuda(cudaError_t e, const char* file, int line)
 {
     snprintf(g_err_file, sizeof(g_err_file), "%s", file);
     g_err_line = line;
@@ -46,34 +39,20 @@ static int fail_cuda(cudaError_t e, const char* file, int line)
     return e == cudaErrorMemoryAllocation ? NNS_B200_ERR_NOMEM : NNS_B200_ERR_CUDA;
 }
 
-#define CU_TRY(call)                                                   \
-    do {                                                               \
-        const cudaError_t e__ = (call);                                \
-        if (e__ != cudaSuccess) return fail_cuda(e__, __FILE__, __LINE__); \
-    } while (0)
-
-#define ST_TRY(call)                        \
-    do {                                    \
-        const int st__ = (call);            \
-        if (st__ != NNS_B200_OK) return st__; \
-    } while (0)
+const char* last_error_text() { return g_err; }
+void last_cuda_error(const char** file, int* line, int* code)
+{
+    *file = g_err_file;
+    *line = g_err_line;
+    *code = g_err_code;
+}
 
 static std::atomic<unsigned long long> g_launches{0};
+void count_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 // planning (pure host logic)
 // ---------------------------------------------------------------------------------------------
-struct Plan {
-    int path;    // 0 low-k, 1 wide, 2 tensor
-    int q;       // queries per thread (low-k)
-    int warps;   // consumer warps per CTA (low-k)
-    int stages;  // ring depth (low-k)
-    int nqb;     // query blocks / groups (grid.x)
-    int splits;  // reference splits (grid.y)
-    int bps;     // reference blocks per split
-    int smem;    // dynamic shared memory bytes
-};
-
 // k <= 32: the split-precision tcgen05 screen (csrc/tensor_search.cu) beats the FP32 screened kernel
 // once the problem amortises its fixed cost (query image, four launches, per-CTA TMEM set-up):
 // B200, profiles/r1_tensor_*: C2 (k = 3, 2.7e11 pairs) 18.6 ms vs 39.9 ms, C3 (k = 16) 0.49 s vs 2.6 s,
@@ -84,10 +63,6 @@ static bool lowk_prefers_tensor(int k, int m, int n)
     const double pairs = (double)m * (double)n;
     return m >= 1024 && pairs >= (k <= 8 ? 4e9 : 2e9);
 }
-
-typedef int (*occ_fn)(void* user, int k, int q, int mode, int warps, int stages);
-
-static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // register estimate used when no device is available to ask (tests / nns_b200_plan)
 static int est_ctas_per_sm(int k, int q, int warps, int stages)
@@ -137,7 +112,7 @@ static int lowk_mode_of(unsigned flags)
     return LOWK_FILTER;
 }
 
-static int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn occ, void* occ_user, Plan* p)
+int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn occ, void* occ_user, Plan* p)
 {
     if (k <= 0 || m < 0 || n < 0) return fail(NNS_B200_ERR_INVALID, "invalid shape k=%d m=%d n=%d", k, m, n);
     if (num_sms <= 0) num_sms = 148;
@@ -248,26 +223,10 @@ static cudaError_t lowk_dispatch(int k, int q, int mode, const LowkArgs& a, int*
 // ---------------------------------------------------------------------------------------------
 // per-device state
 // ---------------------------------------------------------------------------------------------
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-struct DeviceCtx {
-    int device = -1;
-    int num_sms = 0;
-    bool ready = false;
-    std::mutex mu;  // serialises users of the cached buffers/streams of this device
-    cudaStream_t compute = nullptr, copy = nullptr;
-    std::vector<cudaEvent_t> events;
-    DevBuf q, r, index, keys, idx, stats, peer_keys;
-    std::map<std::tuple<int, int, int, int, int>, int> occ_cache;
-};
-
 static std::mutex g_ctx_mu;
 static std::map<int, DeviceCtx*> g_ctx;
 
-static int ctx_get(int device, DeviceCtx** out)
+int ctx_get(int device, DeviceCtx** out)
 {
     if (device < 0) CU_TRY(cudaGetDevice(&device));
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -281,36 +240,37 @@ static int ctx_get(int device, DeviceCtx** out)
         c = it->second;
     }
     if (!c->ready) {
-        int prev = 0;
-        CU_TRY(cudaGetDevice(&prev));
-        CU_TRY(cudaSetDevice(device));
+        DeviceGuard guard;
+        ST_TRY(guard.enter(device));
         cudaDeviceProp prop;
         CU_TRY(cudaGetDeviceProperties(&prop, device));
-        if (prop.major != 10) {
-            cudaSetDevice(prev);
+        if (prop.major != 10)
             return fail(NNS_B200_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
                         device, prop.major, prop.minor);
-        }
         c->num_sms = prop.multiProcessorCount;
-        // the tensor path takes its scratch (query image, candidate records) from the stream-ordered
-        // allocator; keep freed blocks in the pool across synchronisations instead of returning
-        // ~100 MB to the driver after every host-pointer call
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
+        // The tensor path takes its scratch (query image, candidate records) from a PRIVATE
+        // stream-ordered pool: freed blocks stay in the pool across synchronisations (returning ~1 GB
+        // to the driver after every host-pointer call cost 8 ms of a 28 ms call), but only up to
+        // NNS_B200_POOL_KEEP_MB (default 4096), and the process-wide default pool -- which torch and
+        // other co-tenants use -- is left alone.
+        cudaMemPoolProps pp{};
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        CU_TRY(cudaMemPoolCreate(&c->pool, &pp));
+        const char* e = getenv("NNS_B200_POOL_KEEP_MB");
+        unsigned long long keep = (e ? strtoull(e, nullptr, 0) : 4096ull) << 20;
+        CU_TRY(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
         CU_TRY(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
         c->ready = true;
-        CU_TRY(cudaSetDevice(prev));
     }
     *out = c;
     return NNS_B200_OK;
 }
 
-static int buf_reserve(DevBuf* b, size_t bytes)
+int buf_reserve(DevBuf* b, size_t bytes)
 {
     if (bytes <= b->cap) return NNS_B200_OK;
     if (b->p) CU_TRY(cudaFree(b->p));
@@ -319,6 +279,16 @@ static int buf_reserve(DevBuf* b, size_t bytes)
     const size_t want = bytes + bytes / 8 + 256;
     CU_TRY(cudaMalloc(&b->p, want));
     b->cap = want;
+    return NNS_B200_OK;
+}
+
+int ctx_events(DeviceCtx* c, int count)
+{
+    while ((int)c->events.size() < count) {
+        cudaEvent_t ev;
+        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->events.push_back(ev);
+    }
     return NNS_B200_OK;
 }
 
@@ -340,33 +310,43 @@ static int occ_query(void* user, int k, int q, int mode, int warps, int stages)
     return occ;
 }
 
-// The hot path on device-resident data: plan, launch.  `c` supplies num_sms and the occupancy
-// cache; the caller must have made c->device current.
-static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, const float* d_header,
-                          const float* d_blocks, int index_base, u64* d_keys, unsigned flags, cudaStream_t st)
+bool plan_wants_tensor(int k, int m, int n, unsigned flags, int num_sms)
+{
+    if (m <= 0 || n <= 0) return false;
+    Plan p{};
+    if (make_plan(k, m, n, flags, num_sms, nullptr, nullptr, &p) != NNS_B200_OK) return false;
+    return p.path == 2 && tensor_section_floats(k, n) != 0;
+}
+
+int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, const float* d_header,
+                   const float* d_blocks, const float* d_section, int index_base, u64* d_keys, unsigned flags,
+                   cudaStream_t st)
 {
     if (m == 0 || n == 0) return NNS_B200_OK;
+    if (!d_section) {
+        if (flags & NNS_B200_FLAG_FORCE_TENSOR) return fail(NNS_B200_ERR_INVALID, "this index has no tensor section");
+        flags |= (k <= LOWK_MAX_K && m >= 16) ? NNS_B200_FLAG_FORCE_LOWK : NNS_B200_FLAG_FORCE_WIDE;
+    }
     Plan p;
     ST_TRY(make_plan(k, m, n, flags, c->num_sms, occ_query, c, &p));
     const int mode = lowk_mode_of(flags);
     const int nblocks = ceil_div(n, LB);
     if (p.path == 2) {
-        // the tensor section (centre, |r'|^2, BF16 image) follows the FP32 blocks of the whole index
-        const float* d_section = d_blocks + (size_t)nblocks * index_block_floats(k);
         int launches = 0;
         ST_TRY(buf_reserve(&c->stats, 64));
         // per-call status words {candidates, overflow flag, capacity} from the stream-ordered pool: the
         // flag gates the fallback kernel below, so it must not be shared with a search that another
         // stream of this device has in flight
         unsigned* d_status = nullptr;
-        CU_TRY(cudaMallocAsync((void**)&d_status, 64, st));
+        CU_TRY(cudaMallocFromPoolAsync((void**)&d_status, 64, c->pool, st));
         cudaError_t te = tensor_search(k, m, n, d_queries, d_blocks, d_section, index_base, d_keys, mode == LOWK_EXACT_V0,
-                                       c->num_sms, st, &launches, d_status, (flags & NNS_B200_FLAG_TEST_TINY_CANDIDATES) != 0);
-        g_launches.fetch_add((unsigned long long)launches + 1, std::memory_order_relaxed);
-        // Fallback for data whose near-ties overflow the candidate buffer (e.g. all points identical, or
-        // clusters far denser than the BF16 screen resolves): the FP32 kernel of this shape, launched
-        // unconditionally behind the device-side flag the re-score kernel leaves in d_status[1]; it
-        // exits at once when the flag is clear.  No host round trip.
+                                       c->num_sms, st, c->pool, &launches, d_status,
+                                       (flags & NNS_B200_FLAG_TEST_TINY_CANDIDATES) != 0);
+        count_launches((unsigned long long)launches + 1);
+        // Fallback for data whose near-ties overflow the candidate buffer (e.g. all points identical):
+        // the FP32 kernel of this shape, launched unconditionally behind the device-side flag the
+        // re-score kernel leaves in d_status[1]; it exits at once when the flag is clear.  No host
+        // round trip.
         int fst = NNS_B200_OK;
         if (te == cudaSuccess) {
             const int* enable = (const int*)d_status + 1;
@@ -409,112 +389,13 @@ static int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_quer
         a.nqg = p.nqb; a.splits = p.splits; a.stream = st;
         CU_TRY(wide_launch(mode == LOWK_EXACT_V0, a));
     }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return NNS_B200_OK;
-}
-
-struct DeviceGuard {
-    int prev = -1;
-    bool active = false;
-    int enter(int device)
-    {
-        CU_TRY(cudaGetDevice(&prev));
-        if (prev != device) CU_TRY(cudaSetDevice(device));
-        active = true;
-        return NNS_B200_OK;
-    }
-    ~DeviceGuard()
-    {
-        if (active && prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-static unsigned host_flags();
-
-// Host arrays -> device -> keys (h_keys != NULL) or indices (h_idx != NULL) on the host.
-// References are ingested in chunks: the H2D copy of chunk c+1 (copy stream) overlaps the
-// index build + search of chunk c (compute stream); every chunk accumulates into the same
-// packed keys with its own index base.
-static int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, const float* r, int index_base,
-                          u64* h_keys, int* h_idx, u64* ext_keys = nullptr, float* h_dist = nullptr)
-{
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard guard;
-    ST_TRY(guard.enter(c->device));
-    const size_t qbytes = (size_t)m * k * sizeof(float);
-    const size_t rbytes = (size_t)n * k * sizeof(float);
-    const size_t ibytes = nns_b200_index_floats(k, n) * sizeof(float);
-    ST_TRY(buf_reserve(&c->q, qbytes));
-    ST_TRY(buf_reserve(&c->r, rbytes));
-    ST_TRY(buf_reserve(&c->index, ibytes));
-    ST_TRY(buf_reserve(&c->keys, (size_t)m * sizeof(u64)));
-    ST_TRY(buf_reserve(&c->idx, (size_t)m * sizeof(int) * (h_dist ? 2 : 1)));
-    float* d_q = (float*)c->q.p;
-    float* d_r = (float*)c->r.p;
-    float* d_index = (float*)c->index.p;
-    // ext_keys: an already initialised key array, possibly in a PEER GPU's memory (NVLink P2P).
-    // The search accumulates into this GPU's own keys; one merge kernel then atomicMin's them
-    // into ext_keys, i.e. the cross-GPU (dist, idx) reduction is m device-side atomics over NVLink.
-    u64* d_keys = (u64*)c->keys.p;
-    int* d_idx = (int*)c->idx.p;
-
-    CU_TRY(cudaMemcpyAsync(d_q, s, qbytes, cudaMemcpyHostToDevice, c->compute));
-    CU_TRY(launch_keys_init(d_keys, m, c->compute));
-    g_launches.fetch_add(h_idx ? 2 : 1, std::memory_order_relaxed);  // keys init (+ unpack below)
-
-    // chunk = about 32 MiB of AoS reference data, a whole number of reference blocks
-    long long chunk = ((32ll << 20) / ((long long)k * 4)) / LB * LB;
-    if (chunk < LB) chunk = LB;
-    // The tensor section (centre, BF16 operand image) is only built when this call is planned onto the
-    // tcgen05 path; the planner's choice is monotone in n, so the chunks of a search that is not
-    // never pick it either.  The centre needs the whole reference set: one chunk.
-    Plan whole{};
-    if (n > 0) ST_TRY(make_plan(k, m, n, host_flags(), c->num_sms, nullptr, nullptr, &whole));
-    const bool has_tensor = whole.path == 2 && tensor_section_floats(k, n) != 0;
-    if (has_tensor) chunk = ((long long)n + LB - 1) / LB * LB;
-    const int nchunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
-    while ((int)c->events.size() < nchunks) {
-        cudaEvent_t ev;
-        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        c->events.push_back(ev);
-    }
-    for (int ci = 0; ci < nchunks; ++ci) {
-        const long long j0 = (long long)ci * chunk;
-        const int cn = (int)((n - j0) < chunk ? (n - j0) : chunk);
-        CU_TRY(cudaMemcpyAsync(d_r + j0 * k, r + j0 * k, (size_t)cn * k * sizeof(float),
-                               cudaMemcpyHostToDevice, c->copy));
-        CU_TRY(cudaEventRecord(c->events[ci], c->copy));
-        CU_TRY(cudaStreamWaitEvent(c->compute, c->events[ci], 0));
-        float* d_blocks_c = d_index + INDEX_HEADER_FLOATS + (j0 / LB) * (long long)index_block_floats(k);
-        CU_TRY(launch_index_build(k, cn, d_r + j0 * k, d_index, d_blocks_c, ci == 0, c->compute));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        if (has_tensor)
-            CU_TRY(tensor_index_build(k, cn, d_r, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(cn, LB) * index_block_floats(k),
-                                      c->compute));
-        ST_TRY(search_keys_on(c, k, m, cn, d_q, d_index, d_blocks_c, index_base + (int)j0, d_keys, host_flags(),
-                              c->compute));
-    }
-    if (ext_keys) {
-        CU_TRY(launch_keys_merge(ext_keys, d_keys, m, c->compute));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
-    if (h_keys) {
-        CU_TRY(cudaMemcpyAsync(h_keys, d_keys, (size_t)m * sizeof(u64), cudaMemcpyDeviceToHost, c->compute));
-    }
-    if (h_idx) {
-        float* d_dist = h_dist ? (float*)(d_idx + m) : nullptr;  // second half of the idx buffer
-        CU_TRY(launch_keys_unpack(d_keys, m, d_idx, d_dist, c->compute));
-        CU_TRY(cudaMemcpyAsync(h_idx, d_idx, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
-        if (h_dist) CU_TRY(cudaMemcpyAsync(h_dist, d_dist, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
-    }
-    CU_TRY(cudaStreamSynchronize(c->compute));
-    CU_TRY(cudaStreamSynchronize(c->copy));
+    count_launches(1);
     return NNS_B200_OK;
 }
 
 // NNS_B200_FLAGS (environment, a C integer literal) applies the flags word to the host-pointer
 // entry points, whose reference signature has no flags argument.
-static unsigned host_flags()
+unsigned host_flags()
 {
     static const unsigned f = []() {
         const char* e = getenv("NNS_B200_FLAGS");
@@ -523,7 +404,7 @@ static unsigned host_flags()
     return f;
 }
 
-static int check_host_args(int k, int m, int n, const void* s, const void* r, const void* out)
+int check_host_args(int k, int m, int n, const void* s, const void* r, const void* out)
 {
     if (k <= 0 || m < 0 || n < 0) return fail(NNS_B200_ERR_INVALID, "invalid shape k=%d m=%d n=%d", k, m, n);
     if ((long long)k * m > 0x7fffffffLL * 4 || (long long)k * n > 0x7fffffffLL * 4)
@@ -532,22 +413,8 @@ static int check_host_args(int k, int m, int n, const void* s, const void* r, co
     return NNS_B200_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// exported
-// ---------------------------------------------------------------------------------------------
-extern "C" {
-
-int nns_b200_version(void) { return NNS_B200_VERSION; }
-const char* nns_b200_last_error(void) { return g_err; }
-unsigned long long nns_b200_launch_count(void) { return g_launches.load(); }
-
-int nns_b200_init(int device)
-{
-    DeviceCtx* c;
-    return ctx_get(device, &c);
-}
-
-int nns_b200_shutdown(void)
+// used by nns_b200_shutdown
+static void ctx_release_all()
 {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     int prev = -1;
@@ -558,25 +425,57 @@ int nns_b200_shutdown(void)
         if (c->ready && cudaSetDevice(c->device) == cudaSuccess) {
             cudaStreamSynchronize(c->compute);
             cudaStreamSynchronize(c->copy);
-            for (DevBuf* b : {&c->q, &c->r, &c->index, &c->keys, &c->idx, &c->stats, &c->peer_keys}) {
+            for (DevBuf* b : {&c->q, &c->r, &c->index, &c->tsec, &c->keys, &c->idx, &c->stats, &c->peer_keys}) {
                 if (b->p) cudaFree(b->p);
                 b->p = nullptr;
                 b->cap = 0;
             }
+            staging_release(c);
             for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
             c->events.clear();
             cudaStreamDestroy(c->compute);
             cudaStreamDestroy(c->copy);
-            // hand the stream-ordered scratch kept in the device's default pool back to the driver
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+            if (c->pool) cudaMemPoolDestroy(c->pool);
+            c->pool = nullptr;
             cudaGetLastError();
             c->ready = false;
             c->occ_cache.clear();
         }
     }
     if (prev >= 0) cudaSetDevice(prev);
+}
+
+}  // namespace nns
+
+using namespace nns;
+
+// ---------------------------------------------------------------------------------------------
+// exported: lifetime, planning, device-resident building blocks
+// (host-pointer entry points and index handles: ingest.cu; multi-GPU: multi.cu)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int nns_b200_version(void) { return NNS_B200_VERSION; }
+const char* nns_b200_last_error(void) { return last_error_text(); }
+unsigned long long nns_b200_launch_count(void) { return g_launches.load(); }
+
+int nns_b200_init(int device)
+{
+    DeviceCtx* c;
+    return ctx_get(device, &c);
+}
+
+int nns_b200_shutdown(void)
+{
+    ctx_release_all();
     return NNS_B200_OK;
+}
+
+int nns_b200_device_sms(int device)
+{
+    DeviceCtx* c;
+    if (ctx_get(device, &c) != NNS_B200_OK) return -1;
+    return c->num_sms;
 }
 
 size_t nns_b200_index_floats(int k, int n)
@@ -586,15 +485,84 @@ size_t nns_b200_index_floats(int k, int n)
            tensor_section_floats(k, n);
 }
 
+static float* section_of(int k, int n, float* d_index)
+{
+    return tensor_section_floats(k, n) ? d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * index_block_floats(k) : nullptr;
+}
+
 int nns_b200_index_build(int k, int n, const float* d_refs_aos, float* d_index, void* stream)
 {
     if (k <= 0 || n < 0) return fail(NNS_B200_ERR_INVALID, "invalid shape k=%d n=%d", k, n);
     if (n > 0 && (!d_refs_aos || !d_index)) return fail(NNS_B200_ERR_INVALID, "NULL array");
     if (((uintptr_t)d_index & 15) != 0) return fail(NNS_B200_ERR_INVALID, "index must be 16-byte aligned");
-    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_index + INDEX_HEADER_FLOATS, true, (cudaStream_t)stream));
-    CU_TRY(tensor_index_build(k, n, d_refs_aos, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * index_block_floats(k),
-                              (cudaStream_t)stream));
-    g_launches.fetch_add(n > 0 ? 1 : 0, std::memory_order_relaxed);
+    if (n == 0) return NNS_B200_OK;
+    float* d_blocks = d_index + INDEX_HEADER_FLOATS;
+    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_blocks, true, (cudaStream_t)stream));
+    CU_TRY(tensor_index_build(k, n, d_blocks, section_of(k, n, d_index), (cudaStream_t)stream));
+    count_launches(tensor_section_floats(k, n) ? 4 : 1);
+    return NNS_B200_OK;
+}
+
+/* One slice of an index that several GPUs (processes) build together: references [j0, j0 + cn) of an
+ * index laid out for n_total references.  The centre of the tensor section is fixed by the caller so
+ * that every slice uses the same one; the maxima of the slice accumulate in the header words of
+ * `part`.  After the slices have been exchanged (all-gather of the block / image ranges and of the
+ * header words), nns_b200_index_finish folds the partial maxima. */
+int nns_b200_index_build_part(int k, int n_total, int j0, int cn, int part_blocks, const float* d_refs_aos_part,
+                              float* d_index, const float* centre, int part, void* stream)
+{
+    if (k <= 0 || n_total <= 0 || j0 < 0 || cn < 0 || (j0 % LB) != 0 || part_blocks < ceil_div(cn, LB) ||
+        ((long long)j0 / LB + part_blocks) > ceil_div(n_total, LB))
+        return fail(NNS_B200_ERR_INVALID, "invalid part k=%d n=%d j0=%d cn=%d blocks=%d", k, n_total, j0, cn, part_blocks);
+    if (part < 0 || part >= MAX_PEERS) return fail(NNS_B200_ERR_INVALID, "part must be 0..%d", MAX_PEERS - 1);
+    if (!d_index || (cn > 0 && !d_refs_aos_part)) return fail(NNS_B200_ERR_INVALID, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d_section = section_of(k, n_total, d_index);
+    // this GPU's copy of both headers: zero, then the fixed centre
+    TensorCentre c{};
+    if (d_section) {
+        if (!centre) return fail(NNS_B200_ERR_INVALID, "a part of an index with a tensor section needs a fixed centre");
+        for (int t = 0; t < k && t < 128; ++t) c.c[t] = centre[t];
+        CU_TRY(tensor_section_init(k, n_total, nullptr, d_section, &c, st));
+    }
+    BlockDsts dst{};
+    float* d_blocks_part = d_index + INDEX_HEADER_FLOATS + (size_t)(j0 / LB) * index_block_floats(k);
+    dst.p[0] = d_blocks_part;
+    dst.count = 1;
+    CU_TRY(launch_index_build_to(k, cn, d_refs_aos_part, d_index, HDR_PART_MAX + part, dst, true, st, part_blocks));
+    if (d_section) {
+        ImageDsts idst{};
+        idst.p[0] = reinterpret_cast<unsigned char*>(d_section + TENSOR_HDR_FLOATS) + (size_t)(j0 / LB) * tensor_image_bytes_per_block(k);
+        idst.count = 1;
+        CU_TRY(tensor_image_build(k, cn, d_blocks_part, d_section, THDR_PART_MAX + part, THDR_PART_FLAGS + part, idst, st, part_blocks));
+    }
+    count_launches(d_section ? 3 : 1);
+    return NNS_B200_OK;
+}
+
+int nns_b200_index_finish(int k, int n_total, float* d_index, int parts, void* stream)
+{
+    if (k <= 0 || n_total <= 0 || !d_index || parts < 1 || parts > MAX_PEERS) return fail(NNS_B200_ERR_INVALID, "invalid index");
+    CU_TRY(launch_header_fold(d_index, section_of(k, n_total, d_index), parts, (cudaStream_t)stream));
+    count_launches(1);
+    return NNS_B200_OK;
+}
+
+/* byte ranges of an index that a part owns (for the exchange between GPUs): out6 = { blocks offset,
+ * blocks bytes, image offset, image bytes (0 without a tensor section), index-header partial word
+ * offset, section-header partial-max word offset } -- all in bytes from d_index */
+int nns_b200_index_part_ranges(int k, int n_total, int j0, int part_blocks, int part, size_t* out6)
+{
+    if (k <= 0 || n_total <= 0 || !out6 || (j0 % LB) != 0) return fail(NNS_B200_ERR_INVALID, "invalid part");
+    const size_t nb = (size_t)part_blocks, b0 = (size_t)j0 / LB;
+    out6[0] = ((size_t)INDEX_HEADER_FLOATS + b0 * index_block_floats(k)) * 4;
+    out6[1] = nb * index_block_floats(k) * 4;
+    const bool sec = tensor_section_floats(k, n_total) != 0;
+    const size_t sec0 = ((size_t)INDEX_HEADER_FLOATS + (size_t)ceil_div(n_total, LB) * index_block_floats(k)) * 4;
+    out6[2] = sec ? sec0 + TENSOR_HDR_FLOATS * 4 + b0 * tensor_image_bytes_per_block(k) : 0;
+    out6[3] = sec ? nb * tensor_image_bytes_per_block(k) : 0;
+    out6[4] = (size_t)(HDR_PART_MAX + part) * 4;
+    out6[5] = sec ? sec0 + (size_t)(THDR_PART_MAX + part) * 4 : 0;
     return NNS_B200_OK;
 }
 
@@ -602,7 +570,7 @@ int nns_b200_keys_init(uint64_t* d_keys, int m, void* stream)
 {
     if (m < 0 || (m > 0 && !d_keys)) return fail(NNS_B200_ERR_INVALID, "invalid keys");
     CU_TRY(launch_keys_init((u64*)d_keys, m, (cudaStream_t)stream));
-    g_launches.fetch_add(m > 0 ? 1 : 0, std::memory_order_relaxed);
+    count_launches(m > 0 ? 1 : 0);
     return NNS_B200_OK;
 }
 
@@ -610,7 +578,7 @@ int nns_b200_keys_unpack(const uint64_t* d_keys, int m, int* d_idx, float* d_dis
 {
     if (m < 0 || (m > 0 && (!d_keys || !d_idx))) return fail(NNS_B200_ERR_INVALID, "invalid keys");
     CU_TRY(launch_keys_unpack((const u64*)d_keys, m, d_idx, d_dist, (cudaStream_t)stream));
-    g_launches.fetch_add(m > 0 ? 1 : 0, std::memory_order_relaxed);
+    count_launches(m > 0 ? 1 : 0);
     return NNS_B200_OK;
 }
 
@@ -624,8 +592,8 @@ int nns_b200_search_keys(int k, int m, int n, const float* d_queries, const floa
     DeviceCtx* c;
     ST_TRY(ctx_get(-1, &c));
     std::lock_guard<std::mutex> lk(c->mu);
-    return search_keys_on(c, k, m, n, d_queries, d_index, d_index + INDEX_HEADER_FLOATS, index_base, (u64*)d_keys, flags,
-                          (cudaStream_t)stream);
+    return search_keys_on(c, k, m, n, d_queries, d_index, d_index + INDEX_HEADER_FLOATS, section_of(k, n, (float*)d_index),
+                          index_base, (u64*)d_keys, flags, (cudaStream_t)stream);
 }
 
 size_t nns_b200_workspace_bytes(int k, int m, int n)
@@ -651,173 +619,18 @@ int nns_b200_search_device(int k, int m, int n, const float* d_queries, const fl
     ST_TRY(ctx_get(-1, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     CU_TRY(launch_keys_init(d_keys, m, st));
-    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_index + INDEX_HEADER_FLOATS, true, st));
-    // the tensor section only when this search is planned onto the tcgen05 path (as in search_host_on)
-    Plan whole{};
-    if (n > 0) ST_TRY(make_plan(k, m, n, flags, c->num_sms, nullptr, nullptr, &whole));
-    if (whole.path == 2)
-        CU_TRY(tensor_index_build(k, n, d_refs_aos, d_index + INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * index_block_floats(k), st));
-    g_launches.fetch_add(n > 0 ? 3 : 2, std::memory_order_relaxed);  // + the unpack below
-    ST_TRY(search_keys_on(c, k, m, n, d_queries, d_index, d_index + INDEX_HEADER_FLOATS, 0, d_keys, flags, st));
+    float* d_blocks = d_index + INDEX_HEADER_FLOATS;
+    CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_blocks, true, st));
+    // the tensor section only when this search is planned onto the tcgen05 path
+    float* d_section = nullptr;
+    if (plan_wants_tensor(k, m, n, flags, c->num_sms)) {
+        d_section = section_of(k, n, d_index);
+        CU_TRY(tensor_index_build(k, n, d_blocks, d_section, st));
+    }
+    count_launches(n > 0 ? 3 : 2);  // + the unpack below
+    ST_TRY(search_keys_on(c, k, m, n, d_queries, d_index, d_blocks, d_section, 0, d_keys, flags, st));
     CU_TRY(launch_keys_unpack(d_keys, m, d_idx, nullptr, st));
     return NNS_B200_OK;
-}
-
-int nns_b200_search_host(int k, int m, int n, const float* s_points, const float* r_points, int* results)
-{
-    ST_TRY(check_host_args(k, m, n, s_points, r_points, results));
-    if (m == 0) return NNS_B200_OK;
-    DeviceCtx* c;
-    ST_TRY(ctx_get(-1, &c));
-    return search_host_on(c, k, m, n, s_points, r_points, 0, nullptr, results);
-}
-
-int nns_b200_search_host_dist(int k, int m, int n, const float* s_points, const float* r_points, int* results,
-                              float* distances)
-{
-    ST_TRY(check_host_args(k, m, n, s_points, r_points, results));
-    if (m > 0 && !distances) return fail(NNS_B200_ERR_INVALID, "NULL array");
-    if (m == 0) return NNS_B200_OK;
-    DeviceCtx* c;
-    ST_TRY(ctx_get(-1, &c));
-    return search_host_on(c, k, m, n, s_points, r_points, 0, nullptr, results, nullptr, distances);
-}
-
-int nns_b200_search_multi(int k, int m, int n, const float* s_points, const float* r_points, int* results,
-                          int num_gpus, int shard_mode)
-{
-    ST_TRY(check_host_args(k, m, n, s_points, r_points, results));
-    if (shard_mode != 0 && shard_mode != 1) return fail(NNS_B200_ERR_INVALID, "shard_mode must be 0 or 1");
-    if (m == 0) return NNS_B200_OK;
-    int visible = 0;
-    CU_TRY(cudaGetDeviceCount(&visible));
-    if (num_gpus <= 0 || num_gpus > visible) num_gpus = visible;
-    if (num_gpus <= 0) return fail(NNS_B200_ERR_CUDA, "no CUDA device");
-    const int G = num_gpus;
-    std::vector<DeviceCtx*> ctx(G);
-    for (int g = 0; g < G; ++g) ST_TRY(ctx_get(g, &ctx[g]));
-
-    std::vector<int> status(G, NNS_B200_OK);
-    std::vector<std::string> msgs(G);
-    std::vector<std::thread> th;
-    if (shard_mode == 0) {
-        // query-sharded: GPU g answers queries [g*per, ...) against every reference point
-        const int per = ceil_div(m, G);
-        for (int g = 0; g < G; ++g) {
-            th.emplace_back([&, g]() {
-                const int q0 = g * per;
-                const int qn = q0 >= m ? 0 : ((m - q0) < per ? (m - q0) : per);
-                if (qn > 0)
-                    status[g] = search_host_on(ctx[g], k, qn, n, s_points + (size_t)q0 * k, r_points, 0, nullptr,
-                                               results + q0);
-                if (status[g] != NNS_B200_OK) msgs[g] = g_err;
-            });
-        }
-        for (auto& t : th) t.join();
-    } else {
-        // reference-sharded: GPU g owns a contiguous slice of whole reference blocks
-        // (core.cu:781-791 without the <= 0 tail defect D9); packed keys merged by integer MIN
-        const long long blocks = ceil_div(n, LB);
-        const long long per_blocks = (blocks + G - 1) / G;
-        // Reduction over NVLink peer memory: when every GPU can address GPU 0's memory, each GPU
-        // atomicMin's its packed keys straight into ONE key array resident on GPU 0
-        // (keys_merge_kernel) -- no NCCL, no host merge.
-        bool p2p = G > 1;
-        for (int g = 1; g < G && p2p; ++g) {
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, g, 0) != cudaSuccess || !can) p2p = false;
-        }
-        if (p2p) {
-            int prev = 0;
-            CU_TRY(cudaGetDevice(&prev));
-            for (int g = 1; g < G; ++g) {
-                CU_TRY(cudaSetDevice(g));
-                const cudaError_t pe = cudaDeviceEnablePeerAccess(0, 0);
-                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) p2p = false;
-                cudaGetLastError();
-            }
-            CU_TRY(cudaSetDevice(prev));
-        }
-        if (p2p) {
-            DeviceCtx* c0 = ctx[0];
-            u64* shared_keys = nullptr;
-            {
-                std::lock_guard<std::mutex> lk(c0->mu);
-                DeviceGuard guard;
-                ST_TRY(guard.enter(0));
-                ST_TRY(buf_reserve(&c0->peer_keys, (size_t)m * sizeof(u64)));
-                shared_keys = (u64*)c0->peer_keys.p;
-                CU_TRY(launch_keys_init(shared_keys, m, c0->compute));
-                CU_TRY(cudaStreamSynchronize(c0->compute));
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-            }
-            for (int g = 0; g < G; ++g) {
-                th.emplace_back([&, g]() {
-                    const long long r0 = (long long)g * per_blocks * LB;
-                    const long long rn = r0 >= n ? 0 : ((n - r0) < per_blocks * LB ? (n - r0) : per_blocks * LB);
-                    if (rn <= 0) return;
-                    status[g] = search_host_on(ctx[g], k, m, (int)rn, s_points, r_points + r0 * k, (int)r0, nullptr, nullptr,
-                                               shared_keys);
-                    if (status[g] != NNS_B200_OK) msgs[g] = g_err;
-                });
-            }
-            for (auto& t : th) t.join();
-            for (int g = 0; g < G; ++g)
-                if (status[g] != NNS_B200_OK) return fail(status[g], "gpu %d: %s", g, msgs[g].c_str());
-            std::lock_guard<std::mutex> lk(c0->mu);
-            DeviceGuard guard;
-            ST_TRY(guard.enter(0));
-            ST_TRY(buf_reserve(&c0->idx, (size_t)m * sizeof(int)));
-            CU_TRY(launch_keys_unpack(shared_keys, m, (int*)c0->idx.p, nullptr, c0->compute));
-            CU_TRY(cudaMemcpyAsync(results, c0->idx.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c0->compute));
-            CU_TRY(cudaStreamSynchronize(c0->compute));
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            return NNS_B200_OK;
-        }
-        // no peer access: per-GPU keys to the host, merged there
-        std::vector<std::vector<u64>> keys(G);
-        for (int g = 0; g < G; ++g) {
-            th.emplace_back([&, g]() {
-                const long long r0 = (long long)g * per_blocks * LB;
-                const long long rn = r0 >= n ? 0 : ((n - r0) < per_blocks * LB ? (n - r0) : per_blocks * LB);
-                if (rn <= 0) return;
-                keys[g].resize(m);
-                status[g] = search_host_on(ctx[g], k, m, (int)rn, s_points, r_points + r0 * k, (int)r0,
-                                           keys[g].data(), nullptr);
-                if (status[g] != NNS_B200_OK) msgs[g] = g_err;
-            });
-        }
-        for (auto& t : th) t.join();
-        for (int g = 0; g < G; ++g)
-            if (status[g] != NNS_B200_OK) return fail(status[g], "gpu %d: %s", g, msgs[g].c_str());
-        for (int i = 0; i < m; ++i) {
-            u64 best = KEY_INIT;
-            for (int g = 0; g < G; ++g)
-                if (!keys[g].empty() && keys[g][i] < best) best = keys[g][i];
-            results[i] = (int)(unsigned)(best & 0xffffffffull);
-        }
-    }
-    for (int g = 0; g < G; ++g)
-        if (status[g] != NNS_B200_OK) return fail(status[g], "gpu %d: %s", g, msgs[g].c_str());
-    return NNS_B200_OK;
-}
-
-void nns_b200_cudaCall(int k, int m, int n, float* s_points, float* r_points, int** results)
-{
-    // core.cu:31 -- the callee allocates, the caller frees
-    int* out = (int*)malloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
-    const int st = out ? nns_b200_search_host(k, m, n, s_points, r_points, out)
-                       : fail(NNS_B200_ERR_NOMEM, "malloc(%zu) failed", sizeof(int) * (size_t)m);
-    if (st != NNS_B200_OK) {
-        // utils.h:16-26 -- the reference's CHECK prints and exits; there is no status to return
-        if (st == NNS_B200_ERR_CUDA || g_err_line)
-            printf("Error: %s:%d, code:%d, reason: %s \n", g_err_file, g_err_line, g_err_code,
-                   cudaGetErrorString((cudaError_t)g_err_code));
-        else
-            printf("Error: nns_b200: %s \n", g_err);
-        exit(1);
-    }
-    *results = out;
 }
 
 int nns_b200_tensor_stats(unsigned* out3)

@@ -6,9 +6,26 @@
 
 namespace nns {
 
+// ---- headers ----
+// index header (INDEX_HEADER_FLOATS words): [0] max |r|^2 (bits); [HDR_PART_MAX + g] the same of GPU g's slice
+// tensor section header (TENSOR_HDR_FLOATS words): [0..127] centre, [THDR_MAX] max |r'|^2 (bits),
+// [THDR_FLAGS] bit 0: unusable; [THDR_PART_MAX + g], [THDR_PART_FLAGS + g] per-GPU partials (multi-GPU ingest)
+constexpr int MAX_PEERS = 8;
+constexpr int HDR_PART_MAX = 8;
+constexpr int THDR_MAX = 128, THDR_FLAGS = 129, THDR_PART_MAX = 136, THDR_PART_FLAGS = 152;
+struct BlockDsts { float* p[MAX_PEERS]; int count; };            // first block of the part in every destination index
+struct ImageDsts { unsigned char* p[MAX_PEERS]; int count; };    // first tile image of the part in every destination
+struct HeaderPeers { float* header[MAX_PEERS]; float* section[MAX_PEERS]; int count; int self; };
+struct TensorCentre { float c[128]; };                           // a caller-fixed centre, passed by value
+
 // index_build.cu
 cudaError_t launch_index_build(int k, int n, const float* d_refs_aos, float* d_header, float* d_blocks,
                                bool reset_header, cudaStream_t st);
+// the same into several destinations (peer GPUs), max |r|^2 accumulated in header word `hmax_word`
+cudaError_t launch_index_build_to(int k, int n, const float* d_refs_aos, float* d_header, int hmax_word,
+                                  const BlockDsts& dst, bool reset_header, cudaStream_t st, int write_blocks = 0);
+cudaError_t launch_header_publish(const HeaderPeers& hp, int g, cudaStream_t st);
+cudaError_t launch_header_fold(float* d_header, float* d_section, int parts, cudaStream_t st);
 cudaError_t launch_keys_init(u64* d_keys, int m, cudaStream_t st);
 cudaError_t launch_keys_merge(u64* d_dst, const u64* d_src, int m, cudaStream_t st);
 cudaError_t launch_keys_unpack(const u64* d_keys, int m, int* d_idx, float* d_dist, cudaStream_t st);
@@ -35,10 +52,20 @@ constexpr int TENSOR_SPLIT_MAX_K = 42;  // 3k <= 128 contraction columns
 constexpr int TENSOR_HDR_FLOATS = 256;  // [0..127] centre, [128] max |r'|^2 bits, [129] flags
 int tensor_kp(int k);
 size_t tensor_section_floats(int k, int n);
-cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_section, cudaStream_t st);
+size_t tensor_image_bytes_per_block(int k);
+// section header: zeroed, centre = `fixed` or the mean of a strided sample of the n references in d_blocks
+cudaError_t tensor_section_init(int k, int n, const float* d_blocks, float* d_section, const TensorCentre* fixed,
+                                cudaStream_t st);
+// BF16 operand images of the `cn` references in d_blocks_part (whole blocks) into every destination;
+// max |r'|^2 / flags accumulate in words max_word / flag_word of the section header d_hdr
+cudaError_t tensor_image_build(int k, int cn, const float* d_blocks_part, float* d_hdr, int max_word, int flag_word,
+                               const ImageDsts& dst, cudaStream_t st, int write_blocks = 0);
+// section_init (sampled centre) + image_build of the whole index
+cudaError_t tensor_index_build(int k, int n, const float* d_blocks, float* d_section, cudaStream_t st);
+// scratch comes from `pool` (stream-ordered); *launches = kernels launched
 cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
-                          int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, int* launches,
-                          unsigned* d_stats, bool tiny_candidate_buffer);
+                          int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
+                          int* launches, unsigned* d_stats, bool tiny_candidate_buffer);
 
 // lowk_inst_N.cu (N = (k-1)/2)
 cudaError_t lowk_launch_range_0(int k, int q, int mode, const LowkArgs& a, int* occ);

@@ -268,53 +268,72 @@ __device__ __forceinline__ __nv_bfloat16 bf16_part(float x, int part)
 // ---------------------------------------------------------------------------------------------
 // reference-side preparation (part of index_build for k <= 128)
 // ---------------------------------------------------------------------------------------------
-// section header (floats): [0..127] centre, [128] max |r'|^2 (bits), [129] flags (bit 0: unusable)
-__global__ void tensor_colsum_kernel(const float* __restrict__ aos, const int n, const int k, float* __restrict__ sums)
+// The images are built from the FP32 tiled-SoA blocks (coalesced rows; the AoS upload is not needed
+// again), so a tensor section can be added to an index at any time.  Any centre is valid (distances
+// are translation invariant; it only scales the error bound E), so it is the mean of a strided sample
+// of at most TENSOR_CENTRE_BLOCKS reference blocks -- or a centre fixed by the caller, which lets
+// several GPUs / ingest chunks build slices of one section independently.
+constexpr int TENSOR_CENTRE_BLOCKS = 1024;
+
+// grid.x sampled blocks (block b * stride); warp w sums rows w, w + 4, ... of its block
+__global__ void __launch_bounds__(128)
+tensor_colsum_kernel(const float* __restrict__ blocks, const int n, const int k, const int stride,
+                     float* __restrict__ sums, unsigned* __restrict__ count)
 {
-    // grid.x blocks of 256 points; thread t < k sums its dimension over the block's points
-    const long long j0 = (long long)blockIdx.x * 256;
-    const int jn = (int)min((long long)256, n - j0);
-    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+    const long long b = (long long)blockIdx.x * stride;
+    const int jn = (int)min((long long)LB, n - b * LB);
+    if (jn <= 0) return;
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const float* blk = blocks + (size_t)b * (k + 1) * LB;
+    for (int t = warp; t < k; t += 4) {
         float s = 0.0f;
-        for (int j = 0; j < jn; ++j) {
-            const float x = __ldg(aos + (j0 + j) * k + t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int r = lane + 32 * e;
+            const float x = (r < jn) ? __ldg(blk + (size_t)t * LB + r) : 0.0f;
             if (fabsf(x) <= 1e15f) s += x;  // NaN / INF / huge coordinates do not steer the centre
         }
-        atomicAdd(sums + t, s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) atomicAdd(sums + t, s);
     }
+    if (threadIdx.x == 0) atomicAdd(count, (unsigned)jn);
 }
 
-__global__ void tensor_centre_kernel(float* __restrict__ hdr, const int n, const int k)
+__global__ void tensor_centre_kernel(float* __restrict__ hdr, const int k, const TensorCentre fixed, const int use_fixed)
 {
     const int t = threadIdx.x;
     if (t < 128) {
-        float c = (t < k && n > 0) ? hdr[t] / (float)n : 0.0f;
+        const unsigned cnt = reinterpret_cast<const unsigned*>(hdr)[THDR_MAX + 2];  // samples summed by tensor_colsum_kernel
+        float c = use_fixed ? (t < k ? fixed.c[t] : 0.0f) : ((t < k && cnt > 0) ? hdr[t] / (float)cnt : 0.0f);
         if (!(fabsf(c) <= 1e15f)) {  // NaN / INF / huge input: the tensor path is disabled for this index
             c = 0.0f;
-            atomicOr(reinterpret_cast<unsigned*>(hdr) + 129, 1u);
+            atomicOr(reinterpret_cast<unsigned*>(hdr) + THDR_FLAGS, 1u);
         }
         hdr[t] = c;
     }
 }
 
 // one CTA per 128-reference block: BF16 image of r' = fl(r - c) (TensorGeom layout) with |r'|^2
-// (FP32, split into three BF16 terms; +INF for padded lanes) in columns norm_col .. norm_col + 2
+// (FP32, split into three BF16 terms; +INF for padded lanes) in columns norm_col .. norm_col + 2.
+// Like index_build_kernel it can store to the same slice of several peer GPUs' sections.
 __global__ void __launch_bounds__(128)
-tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k, const TensorGeom g,
-                        float* __restrict__ hdr, unsigned char* __restrict__ image)
+tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int k, const TensorGeom g,
+                        float* __restrict__ hdr, const int max_word, const int flag_word, const ImageDsts dst)
 {
     const long long b = blockIdx.x;
     const int row = threadIdx.x;  // one thread per reference
     const long long j = b * T_BN + row;
     const bool valid = j < n;
-    unsigned char* img = image + (size_t)b * image_bytes(T_BN, g.KB, g.KS);
+    const float* col = blocks + (size_t)b * (k + 1) * LB + row;  // coordinate t of this reference: col[t * LB]
+    const size_t img_off = (size_t)b * image_bytes(T_BN, g.KB, g.KS);
     // |r'|^2 first (ascending dimensions), because its columns may share a chunk with data columns
     float rn = 0.0f;
     bool bad = false;
     for (int t = 0; t < k; ++t) {
         float x = 0.0f;
         if (valid) {
-            x = __fsub_rn(__ldg(aos + j * k + t), hdr[t]);
+            x = __fsub_rn(__ldg(col + (size_t)t * LB), hdr[t]);
             // a NaN / INF coordinate only poisons its own column (that reference cannot win in
             // V0 either); finite but huge values would overflow the error-bound arithmetic
             if (fabsf(x) > 1e15f && fabsf(x) < inf_f()) bad = true;
@@ -331,23 +350,24 @@ tensor_ref_image_kernel(const float* __restrict__ aos, const int n, const int k,
         __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int col = ch * 8 + e;
+            const int c = ch * 8 + e;
             int dim, part;
-            image_column(k, g.ndata, col, false, dim, part);
+            image_column(k, g.ndata, c, false, dim, part);
             float x = 0.0f;
-            if (valid && dim >= 0) x = __fsub_rn(__ldg(aos + j * k + dim), hdr[dim]);
+            if (valid && dim >= 0) x = __fsub_rn(__ldg(col + (size_t)dim * LB), hdr[dim]);
             __nv_bfloat16 o = bf16_part(x, part);
-            if (col == g.norm_col) o = n_hi;
-            if (col == g.norm_col + 1) o = n_mid;
-            if (col == g.norm_col + 2) o = n_lo;
+            if (c == g.norm_col) o = n_hi;
+            if (c == g.norm_col + 1) o = n_mid;
+            if (c == g.norm_col + 2) o = n_lo;
             v[e] = o;
         }
-        *reinterpret_cast<uint4*>(img + image_chunk_at(T_BN, g.KB, row, ch)) = *reinterpret_cast<const uint4*>(v);
+        const size_t o = img_off + image_chunk_at(T_BN, g.KB, row, ch);
+        for (int d = 0; d < dst.count; ++d) *reinterpret_cast<uint4*>(dst.p[d] + o) = *reinterpret_cast<const uint4*>(v);
     }
     unsigned bits = (valid && rn < inf_f()) ? __float_as_uint(rn) : 0u;  // NaN / INF norms excluded
     bits = __reduce_max_sync(0xffffffffu, bits);
-    if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + 128, bits);
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned*>(hdr) + 129, 1u);
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + max_word, bits);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned*>(hdr) + flag_word, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -392,7 +412,7 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         //   FP32 accumulation in the MMA     K 2^-23 * 2.02 |q'| |r'|
         //   FP32 |r'|^2 and its 3-term split (K+1) 2^-24 |r'|^2 + 2^-22 |r'|^2
         //   centring + V0 rounding           (K+8) 2^-24 (|q'| + |r'|)^2
-        const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[128]);
+        const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[THDR_MAX]);
         const float a = sqrtf(qn), rmax = sqrtf(r2);
         const float u24 = 5.9604645e-8f;
         // operand rounding: plain BF16 2^-7 (1 + 2^-9) |q'||r'|; split precision drops only
@@ -402,7 +422,7 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         float E = (c_round + (float)KP * 2.04f * 4.7683716e-7f) * a * rmax + (KP + 5) * u24 * r2 +
                   (KP + 8) * u24 * (a + rmax) * (a + rmax);
         E *= 1.05f;
-        const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[129] & 1u) != 0;  // NaN / INF / huge references
+        const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[THDR_FLAGS] & 1u) != 0;  // NaN / INF / huge references
         const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f);  // false for NaN too
         band[q] = usable ? 2.0f * E : inf_f();
         approx_min[q] = f2ord(inf_f());
@@ -423,7 +443,8 @@ struct TensorCand { int q; int unit; float smin; };  // unit = 32 consecutive re
 struct CandBuf {
     TensorCand* rec;       // [n_ctas * region_cap] CTA regions, then [common_cap] common records
     unsigned* cta_count;   // [n_ctas] records used in each CTA region
-    unsigned* counters;    // [0] common records requested, [1] overflow flag, [2] total records emitted
+    unsigned* common_count;  // common records requested (per query batch)
+    unsigned* status;      // per search: [0] total records emitted, [1] overflow flag, [2] record capacity
     unsigned region_cap;   // multiple of 32
     unsigned common_cap;
     unsigned n_ctas;
@@ -435,9 +456,9 @@ __device__ __forceinline__ void cand_emit(const CandBuf& cb, unsigned* s_count, 
     if (slot < cb.region_cap) {
         cb.rec[(size_t)cta * cb.region_cap + slot] = c;
     } else {
-        const unsigned g = atomicAdd(cb.counters, 1u);
+        const unsigned g = atomicAdd(cb.common_count, 1u);
         if (g < cb.common_cap) cb.rec[(size_t)cb.n_ctas * cb.region_cap + g] = c;
-        else cb.counters[1] = 1u;  // out of space: CTAs that have not started yet give up at once
+        else cb.status[1] = 1u;  // out of space: CTAs that have not started yet give up at once
     }
 }
 
@@ -485,7 +506,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     // (one thread reads the flag for the whole CTA: it can flip between two threads' reads, and a CTA
     // of which only some threads leave would hang at the first barrier)
     __shared__ unsigned s_abort;
-    if (threadIdx.x == 0) s_abort = *reinterpret_cast<volatile const unsigned*>(cb.counters + 1);
+    if (threadIdx.x == 0) s_abort = *reinterpret_cast<volatile const unsigned*>(cb.status + 1);
     __syncthreads();
     if (nt <= 0 || s_abort != 0u) {
         if (threadIdx.x == 0) cb.cta_count[cta] = 0;
@@ -720,7 +741,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     if (threadIdx.x == 0) {
         const unsigned used = *s_cand_count;
         cb.cta_count[cta] = min(used, cb.region_cap);
-        atomicAdd(cb.counters + 2, used);
+        atomicAdd(cb.status, used);
     }
 }
 
@@ -734,9 +755,9 @@ tensor_rescore_kernel(const float* __restrict__ queries, const int k, const floa
                       const int index_base, const CandBuf cb, const float* __restrict__ band,
                       const unsigned* __restrict__ approx_min, u64* __restrict__ keys)
 {
-    const unsigned common = cb.counters[0];
-    if (common > cb.common_cap || cb.counters[1] != 0u) {  // the FP32 kernel launched next takes over
-        if (blockIdx.x == 0 && threadIdx.x == 0) cb.counters[1] = 1u;
+    const unsigned common = *cb.common_count;
+    if (common > cb.common_cap || cb.status[1] != 0u) {  // the FP32 kernel launched after the last batch takes over
+        if (blockIdx.x == 0 && threadIdx.x == 0) cb.status[1] = 1u;
         return;
     }
     const int lane = (int)(threadIdx.x & 31);
@@ -805,27 +826,57 @@ int tensor_kp(int k)
     return g.KB * 64 + g.KS * 16;
 }
 
+size_t tensor_image_bytes_per_block(int k)
+{
+    const TensorGeom g = tensor_geom(k);
+    return image_bytes(T_BN, g.KB, g.KS);
+}
+
 size_t tensor_section_floats(int k, int n)
 {
     if (k < 1 || k > TENSOR_MAX_K || n <= 0) return 0;
     const size_t nblocks = (size_t)((n + LB - 1) / LB);
-    const TensorGeom g = tensor_geom(k);
-    return (size_t)TENSOR_HDR_FLOATS + nblocks * image_bytes(T_BN, g.KB, g.KS) / 4;
+    return (size_t)TENSOR_HDR_FLOATS + nblocks * tensor_image_bytes_per_block(k) / 4;
 }
 
-cudaError_t tensor_index_build(int k, int n, const float* d_refs_aos, float* d_section, cudaStream_t st)
+cudaError_t tensor_section_init(int k, int n, const float* d_blocks, float* d_section, const TensorCentre* fixed,
+                                cudaStream_t st)
 {
     if (tensor_section_floats(k, n) == 0) return cudaSuccess;
-    const TensorGeom g = tensor_geom(k);
-    const int nblocks = (n + LB - 1) / LB;
-    float* hdr = d_section;
-    unsigned char* image = reinterpret_cast<unsigned char*>(d_section + TENSOR_HDR_FLOATS);
-    cudaError_t e = cudaMemsetAsync(hdr, 0, TENSOR_HDR_FLOATS * sizeof(float), st);
+    cudaError_t e = cudaMemsetAsync(d_section, 0, TENSOR_HDR_FLOATS * sizeof(float), st);
     if (e != cudaSuccess) return e;
-    tensor_colsum_kernel<<<(n + 255) / 256, 128, 0, st>>>(d_refs_aos, n, k, hdr);
-    tensor_centre_kernel<<<1, 128, 0, st>>>(hdr, n, k);
-    tensor_ref_image_kernel<<<nblocks, 128, 0, st>>>(d_refs_aos, n, k, g, hdr, image);
+    TensorCentre c{};
+    if (fixed) {
+        c = *fixed;
+    } else {
+        const int nblocks = (n + LB - 1) / LB;
+        const int stride = (nblocks + TENSOR_CENTRE_BLOCKS - 1) / TENSOR_CENTRE_BLOCKS;
+        tensor_colsum_kernel<<<(nblocks + stride - 1) / stride, 128, 0, st>>>(d_blocks, n, k, stride, d_section,
+                                                                              reinterpret_cast<unsigned*>(d_section) + THDR_MAX + 2);
+    }
+    tensor_centre_kernel<<<1, 128, 0, st>>>(d_section, k, c, fixed ? 1 : 0);
     return cudaGetLastError();
+}
+
+cudaError_t tensor_image_build(int k, int cn, const float* d_blocks_part, float* d_hdr, int max_word, int flag_word,
+                               const ImageDsts& dst, cudaStream_t st, int write_blocks)
+{
+    const int nb = write_blocks > 0 ? write_blocks : (cn + LB - 1) / LB;
+    if (nb <= 0 || k < 1 || k > TENSOR_MAX_K) return cudaSuccess;
+    const TensorGeom g = tensor_geom(k);
+    tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks_part, cn, k, g, d_hdr, max_word, flag_word, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t tensor_index_build(int k, int n, const float* d_blocks, float* d_section, cudaStream_t st)
+{
+    if (tensor_section_floats(k, n) == 0) return cudaSuccess;
+    cudaError_t e = tensor_section_init(k, n, d_blocks, d_section, nullptr, st);
+    if (e != cudaSuccess) return e;
+    ImageDsts dst{};
+    dst.p[0] = reinterpret_cast<unsigned char*>(d_section + TENSOR_HDR_FLOATS);
+    dst.count = 1;
+    return tensor_image_build(k, n, d_blocks, d_section, THDR_MAX, THDR_FLAGS, dst, st);
 }
 
 // reference tiles per TMA stage / ring depth per operand geometry (stage = G tiles <= 36 KiB)
@@ -849,93 +900,142 @@ static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st,
     return cudaGetLastError();
 }
 
+__global__ void tensor_status_init_kernel(unsigned* __restrict__ status, const unsigned cap, unsigned* __restrict__ common, const int nbatches)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { status[0] = 0u; status[1] = 0u; status[2] = cap; }
+    if (i < nbatches) common[i] = 0u;
+}
+
+// scratch budget of one search (candidate records dominate): NNS_B200_CAND_MB, default 2048
+static size_t tensor_record_budget()
+{
+    static const size_t b = []() {
+        const char* e = getenv("NNS_B200_CAND_MB");
+        size_t mb = e ? (size_t)strtoull(e, nullptr, 0) : 2048;
+        if (mb < 16) mb = 16;
+        return (mb << 20) / sizeof(TensorCand);
+    }();
+    return b;
+}
+
 // Search m queries against the n references of the index section; accumulates into keys.
-// Returns the number of kernels launched through *launches.
+// The queries are processed in batches of at most 4 waves of CTAs, each batch = query image, screen,
+// re-score on the same scratch: the scratch of a search is bounded (tensor_record_budget) however large m
+// is, and a batch can afford up to 1024 candidate records per query -- clustered / duplicated data
+// (BASELINE config C5: ~400 32-reference units per query inside the 2E band at n = 16.7 M) stays on
+// the tensor cores instead of overflowing into the FP32 fallback.
+// d_stats: [0] candidates emitted, [1] overflow flag (the caller launches the FP32 fallback kernel with
+// it as its enable flag), [2] candidate capacity of one batch.
 cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
-                          int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, int* launches,
-                          unsigned* d_stats, bool tiny_candidate_buffer)
+                          int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
+                          int* launches, unsigned* d_stats, bool tiny_candidate_buffer)
 {
     const TensorGeom g = tensor_geom(k);
     const int nblocks = (n + LB - 1) / LB;
     const int strips = (m + T_BM - 1) / T_BM;
     const float* hdr = d_section;
     const unsigned char* rimage = reinterpret_cast<const unsigned char*>(d_section + TENSOR_HDR_FLOATS);
+    if (launches) *launches = 0;
 
-    // reference splits: minimise (waves of one CTA per SM) x (tiles per CTA); every extra split
-    // costs each query one more seed candidate, so ties go to fewer splits
-    auto choose_splits = [&](int smin) {
+    // query batches: at most 4 waves of CTAs each, balanced, whole waves where possible
+    const int max_batch_ctas = 4 * num_sms;
+    // reference splits (chosen for one batch of `bs` strips): minimise (waves of one CTA per SM) x (tiles
+    // per CTA); every extra split costs each query one more seed candidate, so ties go to fewer splits
+    auto choose_splits = [&](int bs, int smin) {
         double best = 1e300;
         int chosen = smin;
         const int smax = std::max(std::min(nblocks, 64), std::min(nblocks, 2 * smin));
         for (int sp = smin; sp <= smax; ++sp) {
             const int t = (nblocks + sp - 1) / sp;
             const int se = (nblocks + t - 1) / t;
-            const double waves = (double)(((long long)strips * se + num_sms - 1) / num_sms);
+            const double waves = (double)(((long long)bs * se + num_sms - 1) / num_sms);
             const double cost = waves * ((double)t + 24.0);  // + per-CTA prologue (A tile, TMEM alloc) in tile units
             if (cost < best * 0.97) { best = cost; chosen = se; }
         }
         return chosen;
     };
-    int splits = choose_splits(1);
+    int batch_strips = strips, nbatches = 1;
+    if (strips > max_batch_ctas) {
+        nbatches = (strips + max_batch_ctas - 1) / max_batch_ctas;
+        batch_strips = (strips + nbatches - 1) / nbatches;
+        batch_strips = std::min(max_batch_ctas, (batch_strips + num_sms - 1) / num_sms * num_sms);
+        nbatches = (strips + batch_strips - 1) / batch_strips;
+    }
+    int splits = choose_splits(batch_strips, 1);
     // If the data overflows the candidate buffer, only the CTAs already running finish their share of
     // the (then useless) pass -- the rest see the flag and exit.  A job of fewer than four waves is
-    // therefore cut into CTAs of at most 16384 tiles (tools/overflow_cost.py: +11 % instead of a whole
-    // wasted pass); such CTAs of one strip run concurrently, each from an unconverged minimum, so
-    // they get first-split sized candidate regions below.
+    // therefore cut into CTAs of at most 16384 tiles; such CTAs of one strip run concurrently, each from
+    // an unconverged minimum, so they get first-split sized candidate regions below.
     bool short_ctas = false;
-    if ((long long)strips * splits < 4LL * num_sms && (nblocks + splits - 1) / splits > 16384) {
-        splits = choose_splits((nblocks + 16383) / 16384);
+    if ((long long)batch_strips * splits < 4LL * num_sms && (nblocks + splits - 1) / splits > 16384) {
+        splits = choose_splits(batch_strips, (nblocks + 16383) / 16384);
         short_ctas = true;
     }
     const int tps = (nblocks + splits - 1) / splits;
     splits = (nblocks + tps - 1) / tps;
 
-    // Candidate capacity.  Every split of a strip emits its first tiles per query, then one record
-    // per running-minimum improvement (~ln tiles) and per unit inside the band: a CTA region holds
-    // 64 / splits + 6 records per query, the common spill region another m + 65536.
+    // Candidate capacity of a batch.  Every split of a strip emits its first tiles per query, then one
+    // record per running-minimum improvement (~ln tiles) and per unit inside the band.  A CTA region
+    // holds at least 64 / splits + 6 (40 for short CTAs) and at most 1024 records per query, as the
+    // budget allows; the common spill region another 64 per query.
     CandBuf cb{};
-    cb.n_ctas = (unsigned)strips * (unsigned)splits;
-    if (tiny_candidate_buffer) {  // test hook: forces the overflow -> wide-kernel fallback
+    cb.n_ctas = (unsigned)batch_strips * (unsigned)splits;
+    const size_t batch_queries = (size_t)batch_strips * T_BM;
+    if (tiny_candidate_buffer) {  // test hook: forces the overflow -> FP32-kernel fallback
         cb.region_cap = 32;
         cb.common_cap = 32;
     } else {
-        size_t region = short_ctas ? (size_t)T_BM * 40 : (((size_t)T_BM * 64 / splits + (size_t)T_BM * 6 + 31) & ~(size_t)31);
-        const size_t max_records = (size_t)1 << 30;
-        if (region * cb.n_ctas > max_records) region = std::max<size_t>(32, (max_records / cb.n_ctas) & ~(size_t)31);
+        const size_t lo = short_ctas ? (size_t)T_BM * 40 : (((size_t)T_BM * 64 / splits + (size_t)T_BM * 6 + 31) & ~(size_t)31);
+        const size_t hi = (size_t)T_BM * 1024;
+        size_t common = std::min<size_t>(batch_queries * 64 + 65536, tensor_record_budget() / 4);
+        size_t region = (tensor_record_budget() - common) / cb.n_ctas & ~(size_t)31;
+        region = std::max(lo, std::min(hi, region));
         cb.region_cap = (unsigned)region;
-        cb.common_cap = (unsigned)std::min<size_t>((size_t)m + 65536, (size_t)1 << 28);
+        cb.common_cap = (unsigned)common;
     }
     const size_t cand_records = (size_t)cb.n_ctas * cb.region_cap + cb.common_cap;
 
-    // stream-ordered scratch: query image, band, approx_min, counters, per-CTA counts, candidates
-    const size_t qimg_bytes = (size_t)strips * image_bytes(T_BM, g.KB, g.KS);
+    // stream-ordered scratch of one batch: query image, band, approx_min, per-CTA counts, candidates;
+    // + one common-record counter per batch
+    const size_t qimg_bytes = (size_t)batch_strips * image_bytes(T_BM, g.KB, g.KS);
     const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
-    const size_t off_amin = off_band + (((size_t)m * 4 + 255) & ~(size_t)255);
-    const size_t off_cnt = off_amin + (((size_t)m * 4 + 255) & ~(size_t)255);
-    const size_t off_ccnt = off_cnt + 256;
+    const size_t off_amin = off_band + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_cnt = off_amin + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_ccnt = off_cnt + (((size_t)nbatches * 4 + 255) & ~(size_t)255);
     const size_t off_cand = off_ccnt + (((size_t)cb.n_ctas * 4 + 255) & ~(size_t)255);
     const size_t total = off_cand + cand_records * sizeof(TensorCand);
     unsigned char* scratch = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&scratch, total, st);
+    cudaError_t e = pool ? cudaMallocFromPoolAsync((void**)&scratch, total, pool, st) : cudaMallocAsync((void**)&scratch, total, st);
     if (e != cudaSuccess) return e;
     float* band = reinterpret_cast<float*>(scratch + off_band);
     unsigned* amin = reinterpret_cast<unsigned*>(scratch + off_amin);
-    cb.counters = reinterpret_cast<unsigned*>(scratch + off_cnt);
+    unsigned* common_counts = reinterpret_cast<unsigned*>(scratch + off_cnt);
     cb.cta_count = reinterpret_cast<unsigned*>(scratch + off_ccnt);
     cb.rec = reinterpret_cast<TensorCand*>(scratch + off_cand);
+    cb.status = d_stats;
 
-    e = cudaMemsetAsync(cb.counters, 0, 256, st);
-    if (e == cudaSuccess) {
-        tensor_query_image_kernel<<<strips, 256, 0, st>>>(d_queries, m, k, g, hdr, scratch, band, amin);
+    tensor_status_init_kernel<<<(nbatches + 255) / 256, 256, 0, st>>>(d_stats, (unsigned)std::min<size_t>(cand_records, 0xffffffffu),
+                                                                      common_counts, nbatches);
+    e = cudaGetLastError();
+    int nl = 1;
+    // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
+    // CTA is resident per SM even at KP = 64
+    const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
+    for (int b = 0; b < nbatches && e == cudaSuccess; ++b) {
+        const int s0 = b * batch_strips;
+        const int bs = std::min(batch_strips, strips - s0);
+        const long long q0 = (long long)s0 * T_BM;
+        const int bm = (int)std::min<long long>((long long)bs * T_BM, (long long)m - q0);
+        const float* bq = d_queries + (size_t)q0 * k;
+        cb.common_count = common_counts + b;
+        cb.n_ctas = (unsigned)bs * (unsigned)splits;  // the common region follows the regions actually used
+        tensor_query_image_kernel<<<bs, 256, 0, st>>>(bq, bm, k, g, hdr, scratch, band, amin);
         e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) {
-        // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
-        // CTA is resident per SM even at KP = 64
-        const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
-        dim3 grid((unsigned)strips, (unsigned)splits);
+        if (e != cudaSuccess) break;
+        dim3 grid((unsigned)bs, (unsigned)splits);
 #define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_) \
-    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_>(grid, smem, st, scratch, m, rimage, nblocks, tps, band, amin, cb)
+    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_>(grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb)
         if (g.KB == 0 && g.KS == 1) e = NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB);
         else if (g.KB == 0) e = NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB);
         else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1, 1);
@@ -943,24 +1043,16 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         else if (g.KS == 0) e = NNS_SCREEN(2, 0, 4, 1, 1);
         else e = NNS_SCREEN(2, 1, 4, 1, 1);
 #undef NNS_SCREEN
-    }
-    if (e == cudaSuccess) {
+        if (e != cudaSuccess) break;
         const int rgrid = num_sms * 8;
         if (exact)
-            tensor_rescore_kernel<true><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cb, band, amin, d_keys);
+            tensor_rescore_kernel<true><<<rgrid, 256, 0, st>>>(bq, k, d_blocks, index_base, cb, band, amin, d_keys + q0);
         else
-            tensor_rescore_kernel<false><<<rgrid, 256, 0, st>>>(d_queries, k, d_blocks, index_base, cb, band, amin, d_keys);
+            tensor_rescore_kernel<false><<<rgrid, 256, 0, st>>>(bq, k, d_blocks, index_base, cb, band, amin, d_keys + q0);
         e = cudaGetLastError();
+        nl += 3;
     }
-    if (launches) *launches = 3;
-    // d_stats: [0] candidates emitted, [1] overflow flag (the caller launches the FP32 fallback kernel with
-    // it as its enable flag), [2] candidate capacity
-    if (e == cudaSuccess) {
-        const unsigned cap = (unsigned)std::min<size_t>(cand_records, 0xffffffffu);
-        e = cudaMemcpyAsync(d_stats, cb.counters + 2, sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stats + 1, cb.counters + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stats + 2, &cap, sizeof(unsigned), cudaMemcpyHostToDevice, st);
-    }
+    if (launches) *launches = nl;
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;
 }

@@ -74,6 +74,15 @@ lib.nns_b200_workspace_bytes.argtypes = [c_int, c_int, c_int]
 lib.nns_b200_workspace_bytes.restype = c_size_t
 lib.nns_b200_search_device.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]
 lib.nns_b200_tensor_stats.argtypes = [POINTER(c_uint)]
+lib.nns_b200_device_sms.argtypes = [c_int]
+lib.nns_b200_index_create.argtypes = [c_int, c_int, c_void_p, c_int, POINTER(c_void_p)]
+lib.nns_b200_index_search.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+lib.nns_b200_index_size.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
+lib.nns_b200_index_destroy.argtypes = [c_void_p]
+lib.nns_b200_sample_centre.argtypes = [c_int, c_int, c_void_p, c_void_p]
+lib.nns_b200_index_build_part.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+lib.nns_b200_index_part_ranges.argtypes = [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]
+lib.nns_b200_index_finish.argtypes = [c_int, c_int, c_void_p, c_int, c_void_p]
 lib.nns_b200_plan.argtypes = [c_int, c_int, c_int, c_uint, c_int, POINTER(c_int)]
 
 
@@ -131,6 +140,52 @@ def search_multi(k: int, m: int, n: int, s_points, r_points, num_gpus: int = 0, 
     out = np.empty(m, dtype=np.int32)
     _check(lib.nns_b200_search_multi(k, m, n, s.ctypes.data, r.ctypes.data, out.ctypes.data, num_gpus, shard_mode))
     return out
+
+
+class HostIndex:
+    """nns_b200_index_*: the reference set ingested once from a host array and kept resident in HBM;
+    searches take host query arrays (numpy, or raw host pointers as ints) like the drop-in symbol."""
+
+    def __init__(self, k: int, n: int, r_points, device: int = -1):
+        self.k, self.n = int(k), int(n)
+        rp = r_points if isinstance(r_points, int) else _host_f32(r_points, n, k).ctypes.data
+        h = c_void_p()
+        _check(lib.nns_b200_index_create(k, n, rp, device, ctypes.byref(h)))
+        self._h = h
+
+    def search(self, m: int, s_points, out: np.ndarray | None = None, return_dist: bool = False):
+        keep = s_points
+        sp = s_points if isinstance(s_points, int) else _host_f32(s_points, m, self.k).ctypes.data
+        if out is None:
+            out = np.empty(m, dtype=np.int32)
+        dist = np.empty(m, dtype=np.float32) if return_dist else None
+        _check(lib.nns_b200_index_search(self._h, m, sp, out.ctypes.data, dist.ctypes.data if return_dist else None))
+        del keep
+        return (out, dist) if return_dist else out
+
+    def close(self):
+        if self._h:
+            _check(lib.nns_b200_index_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sample_centre(k: int, n: int, r_points) -> np.ndarray:
+    """nns_b200_sample_centre: the common centre of the tcgen05 operand images when several GPUs build
+    slices of one index (host arithmetic over <= 4096 sample rows)."""
+    rp = r_points if isinstance(r_points, int) else _host_f32(r_points, n, k).ctypes.data
+    out = np.zeros(max(k, 1), dtype=np.float32)
+    _check(lib.nns_b200_sample_centre(k, n, rp, out.ctypes.data))
+    return out
+
+
+def device_sms(device: int = -1) -> int:
+    return int(lib.nns_b200_device_sms(device))
 
 
 def plan(k: int, m: int, n: int, flags: int = 0, num_sms: int = 148) -> dict:
@@ -203,6 +258,13 @@ class DeviceIndex:
         self.index = torch.empty(max(nfl, 4), dtype=torch.float32, device=refs.device)
         with torch.cuda.device(self.device):
             _check(lib.nns_b200_index_build(self.k, self.n, refs.data_ptr(), self.index.data_ptr(), _stream_ptr(stream)))
+
+    @classmethod
+    def from_built(cls, index, k: int, n: int, index_base: int = 0):
+        """Wrap an index tensor that was built elsewhere (nns_b200_index_build_part + exchange + finish)."""
+        self = cls.__new__(cls)
+        self.n, self.k, self.index_base, self.device, self.index = int(n), int(k), int(index_base), index.device, index
+        return self
 
     def new_keys(self, m: int, stream=None):
         import torch

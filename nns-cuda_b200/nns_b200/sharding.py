@@ -63,3 +63,55 @@ def allgather_indices(idx_local, m: int, world: int):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat(out)[:m]
+
+
+def gather_built_index(k: int, n: int, r_host, rank: int, world: int, device, stream=None):
+    """Query-sharded search needs the whole reference index on every GPU.  Instead of `world` uploads
+    of the full set (what the reference does, core.cu:793-818), rank g uploads only slice g over its
+    own PCIe link, builds that slice of the index -- FP32 blocks and tcgen05 operand images, with a
+    common centre -- in place (nns_b200_index_build_part), and the built slices are exchanged with
+    in-place NCCL all-gathers over NVLink; nns_b200_index_finish folds the per-slice maxima.
+
+    r_host: the host reference array [n][k] (numpy, or a pinned torch CPU tensor).  Returns a
+    DeviceIndex over n_pad >= n references (equal-sized slices; the padding is NaN and never wins).
+    """
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    import nns_b200
+    from nns_b200 import lib, _check
+
+    r_t = r_host if isinstance(r_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(r_host, dtype=np.float32))
+    r_np = r_t.numpy()
+    blocks = (n + REF_BLOCK - 1) // REF_BLOCK
+    per_blocks = (blocks + world - 1) // world
+    n_pad = per_blocks * world * REF_BLOCK
+    j0 = rank * per_blocks * REF_BLOCK
+    cn = max(0, min(n - j0, per_blocks * REF_BLOCK))
+    st = stream if stream is not None else torch.cuda.current_stream()
+    index = torch.empty(nns_b200.index_floats(k, n_pad), dtype=torch.float32, device=device)
+    with torch.cuda.device(device), torch.cuda.stream(st):
+        d_part = r_t[j0:j0 + cn].to(device, non_blocking=True) if cn > 0 else torch.empty((0, k), dtype=torch.float32, device=device)
+        centre = nns_b200.sample_centre(k, n, r_np) if k <= 128 else None
+        _check(lib.nns_b200_index_build_part(k, n_pad, j0, cn, per_blocks, d_part.data_ptr(), index.data_ptr(),
+                                             centre.ctypes.data if centre is not None else None, rank, ctypes.c_void_p(st.cuda_stream)))
+        if world > 1:
+            rg = (ctypes.c_size_t * 6)()
+            _check(lib.nns_b200_index_part_ranges(k, n_pad, 0, per_blocks, 0, rg))
+            b_off, b_bytes, i_off, i_bytes, h_off, s_off = (int(x) for x in rg)
+            raw = index.view(torch.uint8)
+
+            def gather(off, nbytes):
+                whole = raw[off:off + nbytes * world]
+                dist.all_gather_into_tensor(whole, whole[rank * nbytes:(rank + 1) * nbytes])
+
+            gather(b_off, b_bytes)
+            gather(h_off, 4)
+            if i_bytes:
+                gather(i_off, i_bytes)
+                gather(s_off, 4)        # partial max |r'|^2
+                gather(s_off + 64, 4)   # partial flags
+        _check(lib.nns_b200_index_finish(k, n_pad, index.data_ptr(), world, ctypes.c_void_p(st.cuda_stream)))
+    return nns_b200.DeviceIndex.from_built(index, k, n_pad)

@@ -25,6 +25,12 @@ sed -n '55,56p' "$REF/core.cu" | grep -q 'v1' || { echo "build_ref: core.cu:55-5
 { printf '#include <math.h>\n#include <stdlib.h>\n'; sed -n '11,54p' "$REF/core.cu"; cat "$HERE/ref_v0_shim_tail.inc"; } |
     /usr/bin/g++ -x c++ - -O3 -ffp-contract=off -fopenmp -fPIC -shared -o "$OUT/libv0_ref.so"
 echo "built $OUT/libv0_ref.so"
+#  * ref_gpu_probe (needs nvcc): oracle/ref_gpu_probe.cu (our driver) + the reference's core.cu included by
+#    path, one variant on one shape with the reference's generator and timing; bench.py's `ref_gpu` record.
+if command -v nvcc >/dev/null && [ ! -x "$OUT/ref_gpu_probe" -o "$HERE/ref_gpu_probe.cu" -nt "$OUT/ref_gpu_probe" ]; then
+    nvcc -O2 -Xcompiler -fopenmp -arch=sm_100a -include thrust/extrema.h -I"$REF" "$HERE/ref_gpu_probe.cu" -o "$OUT/ref_gpu_probe" 2>/dev/null \
+        && echo "built $OUT/ref_gpu_probe" || echo "build_ref: ref_gpu_probe did not build (optional)" >&2
+fi
 if [ "${BUILD_REF_MAIN:-1}" = "1" ] && command -v nvcc >/dev/null; then
     nvcc -Xcompiler -fopenmp -arch=sm_100a -include thrust/extrema.h -I"$REF" "$REF/main.cu" -o "$OUT/ref_main" 2>/dev/null \
         && echo "built $OUT/ref_main" || echo "build_ref: ref_main did not build (optional)" >&2

@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "liboracle_v0.so")
 REF_SO = os.path.join(HERE, "_ref", "libv0_ref.so")
+REF_PROBE = os.path.join(HERE, "_ref", "ref_gpu_probe")
 
 
 def build(force: bool = False) -> None:
@@ -20,7 +21,10 @@ def build(force: bool = False) -> None:
     the real reference V0 into oracle/_ref/ (build_ref.sh)."""
     if force or not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(HERE, "v0_oracle.c")):
         subprocess.check_call(["make", "-C", HERE, "liboracle_v0.so"], stdout=subprocess.DEVNULL)
-    if os.path.exists("/root/reference/core.cu") and (force or not os.path.exists(REF_SO)):
+    probe_stale = (not os.path.exists(REF_PROBE)
+                   or os.path.getmtime(REF_PROBE) < os.path.getmtime(os.path.join(HERE, "ref_gpu_probe.cu"))
+                   or os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_v0_shim_tail.inc"))) if os.path.exists(REF_SO) else True
+    if os.path.exists("/root/reference/core.cu") and (force or not os.path.exists(REF_SO) or probe_stale):
         env = dict(os.environ, BUILD_REF_MAIN="0")
         subprocess.check_call([os.path.join(HERE, "build_ref.sh")], env=env, stdout=subprocess.DEVNULL)
 
@@ -41,6 +45,8 @@ def port():
         lib.oracle_v0_search_omp.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int]
         lib.oracle_v0_search_omp.restype = c_int
         lib.oracle_num_threads.restype = c_int
+        lib.oracle_set_threads.argtypes = [c_int]
+        lib.oracle_set_threads.restype = None
         lib.oracle_check_tie_rule.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, POINTER(c_long)]
         lib.oracle_check_tie_rule.restype = c_long
         _port = lib
@@ -57,8 +63,22 @@ def ref():
         lib.ref_v0_search_omp.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int]
         lib.ref_v0_search_omp.restype = c_int
         lib.ref_num_threads.restype = c_int
+        if hasattr(lib, "ref_set_threads"):
+            lib.ref_set_threads.argtypes = [c_int]
+            lib.ref_set_threads.restype = None
         _ref = lib
     return _ref
+
+
+def set_threads(n: int) -> int:
+    """Team size of the OpenMP wrappers (both libraries share one libgomp).  torchrun exports
+    OMP_NUM_THREADS=1, so the bench legs that time V0 on "all host cores" say so explicitly."""
+    n = int(n) if n and n > 0 else (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    port().oracle_set_threads(n)
+    r = ref()
+    if r is not None and hasattr(r, "ref_set_threads"):
+        r.ref_set_threads(n)
+    return n
 
 
 def _f32(a, rows, k):

@@ -82,6 +82,16 @@ int oracle_v0_search_omp(int k, int m, int n, const float *s_points, const float
     return threads;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the bench sets the team size it reports explicitly */
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(nns):
     assert len(syms) >= 15
     for s in syms:
         assert hasattr(nns.lib, s), f"{s} declared in include/nns_b200.h but not exported"
-    assert nns.lib.nns_b200_version() == 100
+    assert nns.lib.nns_b200_version() == 200
 
 
 def test_header_constants_match_binding(nns):

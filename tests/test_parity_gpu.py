@@ -466,3 +466,153 @@ def test_c5_construction_at_one_million_points(nns, oracle, torch_mod):
     # all duplicated-point queries found a zero-distance reference with the lowest index among its copies
     dup = np.arange(0, m, 2)
     assert np.array_equal(r[g[dup]], s[dup])
+
+
+# ---- round 2: ingest, handles, batching, multi-GPU ---------------------------------------------
+def test_pageable_staging_and_pinned_sources_agree(nns, oracle, torch_mod):
+    """The host-pointer ABI takes pageable arrays (the reference passes malloc'd memory, main.cu:27-34)
+    through the pinned staging ring -- > 3 slots of 8 MiB here, so slots are reused -- and pinned ones
+    straight to the copy engine; both must give V0's answer."""
+    torch = torch_mod
+    k, m, n = 16, 700, 600_000  # 36.6 MiB of references
+    s, r = make_case("uniform", k, m, n, 21)
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    g_pageable = nns.search_host(k, m, n, s, r)
+    rep = oracle.check_tie_rule(k, m, n, s, r, g_pageable, v, REL_TOL)
+    assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= m - 1, rep
+    sp, rp = torch.from_numpy(s).pin_memory(), torch.from_numpy(r).pin_memory()
+    g_pinned = nns.search_host(k, m, n, sp.data_ptr(), rp.data_ptr())
+    assert np.array_equal(g_pinned, g_pageable)
+
+
+def test_chunked_ingest_on_the_tensor_path(nns, oracle):
+    """A host-pointer call that is planned onto the tcgen05 screen ingests the references in chunks too
+    (every chunk is an index of its own: own centre, own operand images): k = 16, 32 MiB -> 2 chunks."""
+    k, m, n = 16, 4096, 500_000
+    assert nns.plan(k, m, n)["path"] == 2
+    s, r = make_case("uniform", k, m, n, 22)
+    sample = np.random.default_rng(2).permutation(m)[:256]
+    v, _ = oracle.v0_omp(k, 256, n, s[sample], r)
+    g = nns.search_host(k, m, n, s, r)
+    rep = oracle.check_tie_rule(k, 256, n, s[sample], r, g[sample], v, REL_TOL)
+    assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= 255, rep
+    assert nns.tensor_stats()["overflow"] == 0
+    # the same answer from the FP32 kernel (one index, no chunks)
+    import torch
+    idx = nns.DeviceIndex(dev(torch, r)).search(dev(torch, s), nns.FLAG_FORCE_LOWK).cpu().numpy()
+    assert np.array_equal(g, idx), int((g != idx).sum())
+
+
+@pytest.mark.parametrize("kind,k,m,n", [("clustered", 3, 3000, 250_000), ("uniform", 128, 600, 30_000), ("grid", 16, 2000, 70_000)])
+def test_host_index_handle_build_once_query_many(nns, oracle, kind, k, m, n):
+    """nns_b200_index_create / _search / _destroy: the index stays resident; repeated searches (with and
+    without distances) return V0's answer."""
+    s, r = make_case(kind, k, m, n, 31)
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    h = nns.HostIndex(k, n, r)
+    for rep_i in range(3):
+        if rep_i == 1:
+            g, d = h.search(m, s, return_dist=True)
+            e = (s.astype(np.float64) - r[g].astype(np.float64))
+            np.testing.assert_allclose(d, (e * e).sum(1), rtol=1e-5, atol=1e-12)
+        else:
+            g = h.search(m, s)
+        rep = oracle.check_tie_rule(k, m, n, s, r, g, v, REL_TOL)
+        assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= m - 2, rep
+    # a second, smaller query batch on the same handle
+    g2 = h.search(17, s[5:22])
+    assert np.array_equal(g2, g[5:22])
+    h.close()
+    # empty index: V0 reports 0
+    h0 = nns.HostIndex(k, 0, r[:0])
+    assert h0.search(4, s[:4]).tolist() == [0, 0, 0, 0]
+    h0.close()
+
+
+def test_tensor_path_query_batches(nns, oracle, torch_mod):
+    """More than 4 waves of 256-query strips are searched in batches on a bounded scratch: the keys must
+    equal the FP32 kernel's for every query of every batch."""
+    torch = torch_mod
+    k, n = 3, 30_000
+    m = 256 * (4 * nns.device_sms() + 37) + 11  # two batches, the second ragged
+    s, r = make_case("clustered", k, m, n, 41)
+    index = nns.DeviceIndex(dev(torch, r))
+    dq = dev(torch, s)
+    a = index.search(dq, nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+    assert nns.tensor_stats()["overflow"] == 0
+    b = index.search(dq, nns.FLAG_FORCE_LOWK | nns.FLAG_V0_ROUNDING).cpu().numpy()
+    assert np.array_equal(a, b), int((a != b).sum())
+    sample = np.random.default_rng(4).permutation(m)[:512]
+    v, _ = oracle.v0_omp(k, 512, n, s[sample], r)
+    assert np.array_equal(a[sample], v)
+
+
+def test_dense_clusters_stay_on_the_tensor_screen(nns, oracle, torch_mod):
+    """BASELINE config C5's construction at n = 2^22: hundreds of 32-reference units per query fall
+    inside the screen's 2E band.  The candidate capacity of a batch absorbs them (no overflow, no FP32
+    fallback) and the result is V0's."""
+    torch = torch_mod
+    k, m, n = 3, 1 << 16, 1 << 22
+    s, r = make_case("clustered", k, m, n, 1000)
+    index = nns.DeviceIndex(dev(torch, r))
+    g = index.search(dev(torch, s)).cpu().numpy()
+    st = nns.tensor_stats()
+    print("C5-style @ 2^22 tensor stats:", st)
+    assert nns.plan(k, m, n)["path"] == 2 and st["overflow"] == 0, st
+    sample = np.random.default_rng(6).permutation(m)[:512]
+    v, _ = oracle.v0_omp(k, 512, n, s[sample], r)
+    assert np.array_equal(g[sample], v), int((g[sample] != v).sum())
+    assert np.array_equal(g, index.search(dev(torch, s), nns.FLAG_FORCE_LOWK).cpu().numpy())
+
+
+@pytest.mark.parametrize("kind,k,m,n", [("clustered", 3, 5000, 300_000), ("uniform", 16, 3000, 1_200_000), ("uniform", 128, 4096, 70_000)])
+def test_search_multi_gpu_counts_and_modes(nns, oracle, torch_mod, kind, k, m, n):
+    """nns_b200_search_multi on 1, 2, 4, 8 ... visible GPUs, both shardings: query-sharded uses the
+    sharded ingest whose build kernels store every slice into all peers' indices (fused NVLink
+    all-gather); reference-sharded folds the packed keys into GPU 0 with system-scope red.min.  Needs
+    >= 2 visible GPUs to be more than a smoke test (the G = 1 legs always run)."""
+    ngpu = torch_mod.cuda.device_count()
+    s, r = make_case(kind, k, m, n, 1000)
+    sample = np.random.default_rng(8).permutation(m)[:384]
+    v, _ = oracle.v0_omp(k, 384, n, s[sample], r)
+    base = None
+    for g in [x for x in (1, 2, 3, 4, 8) if x <= ngpu]:
+        for mode in (0, 1):
+            out = nns.search_multi(k, m, n, s, r, num_gpus=g, shard_mode=mode)
+            if kind == "uniform":
+                rep = oracle.check_tie_rule(k, 384, n, s[sample], r, out[sample], v, REL_TOL)
+                assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= 383, (g, mode, rep)
+            else:
+                assert np.array_equal(out[sample], v), (g, mode, int((out[sample] != v).sum()))
+            if base is None:
+                base = out
+            # identical for every GPU count and sharding on tie-free / grid-snapped data
+            assert np.array_equal(out, base) or kind == "uniform" and (out != base).sum() <= 2, (g, mode, int((out != base).sum()))
+
+
+def test_index_parts_and_nccl_gather_world1(nns, oracle, torch_mod):
+    """nns_b200_index_build_part + exchange + nns_b200_index_finish (sharding.gather_built_index) with a
+    one-rank NCCL group: the gathered index must answer like an index built in one piece.  (The world > 1
+    exchange is the same code with all-gathers over NVLink; bench.py --gpus N exercises it.)"""
+    torch = torch_mod
+    import torch.distributed as dist
+
+    from nns_b200 import sharding
+
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        for (k, m, n) in [(3, 4096, 100_000), (128, 1024, 20_000)]:
+            s, r = make_case("uniform", k, m, n, 51)
+            v, _ = oracle.v0_omp(k, m, n, s, r)
+            index = sharding.gather_built_index(k, n, r, 0, 1, torch.device("cuda", 0))
+            for flags in (nns.FLAG_V0_ROUNDING, nns.FLAG_V0_ROUNDING | nns.FLAG_FORCE_TENSOR):
+                g = index.search(dev(torch, s), flags).cpu().numpy()
+                assert np.array_equal(g, v), (k, flags, int((g != v).sum()))
+    finally:
+        if created:
+            dist.destroy_process_group()
