@@ -151,6 +151,21 @@ int nns_b200_search_keys(int k, int m, int n, const float *d_queries, const floa
 /* d_idx[i] = low 32 bits of keys[i]; d_dist[i] = the FP32 squared distance (may be NULL). */
 int nns_b200_keys_unpack(const uint64_t *d_keys, int m, int *d_idx, float *d_dist, void *stream);
 
+/* ---- K nearest neighbours (extension: the reference returns one index per query, core.cu:52) ------
+ * For each query the K <= 32 references with the smallest FP32 squared distance (V0's form,
+ * core.cu:38-43), ordered by (distance, index): ties go to the lower index, so K = 1 is the 1-NN
+ * answer.  References at distance NaN / +INF are never reported; missing neighbours (n < K) are
+ * index -1, distance +INF.
+ * nns_b200_topk_keys: d_keys is uint64[m][K], ascending packed keys, initialised with
+ * nns_b200_keys_init(d_keys, m * K); calls for several reference shards accumulate like
+ * nns_b200_search_keys does.  nns_b200_topk_unpack writes int[m][K] (+ float[m][K]).
+ * nns_b200_search_topk_host: host arrays in, host int[m][K] (+ float[m][K], may be NULL) out. */
+int nns_b200_topk_keys(int k, int m, int n, int K, const float *d_queries, const float *d_index,
+                       int index_base, uint64_t *d_keys, unsigned flags, void *stream);
+int nns_b200_topk_unpack(const uint64_t *d_keys, int m, int K, int *d_idx, float *d_dist, void *stream);
+int nns_b200_search_topk_host(int k, int m, int n, int K, const float *s_points,
+                              const float *r_points, int *indices, float *distances);
+
 /* Convenience: index_build + keys_init + search_keys + keys_unpack on device arrays.
  * d_workspace must hold nns_b200_workspace_bytes(k, m, n) bytes (256-byte aligned). */
 size_t nns_b200_workspace_bytes(int k, int m, int n);

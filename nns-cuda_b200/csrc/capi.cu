@@ -596,6 +596,38 @@ int nns_b200_search_keys(int k, int m, int n, const float* d_queries, const floa
                           index_base, (u64*)d_keys, flags, (cudaStream_t)stream);
 }
 
+int nns_b200_topk_keys(int k, int m, int n, int K, const float* d_queries, const float* d_index, int index_base,
+                       uint64_t* d_keys, unsigned flags, void* stream)
+{
+    if (k <= 0 || k > TOPK_MAX_DIMS || m < 0 || n < 0) return fail(NNS_B200_ERR_INVALID, "invalid shape k=%d m=%d n=%d", k, m, n);
+    if (K < 1 || K > TOPK_MAX_K) return fail(NNS_B200_ERR_UNSUPPORTED, "K must be 1..%d", TOPK_MAX_K);
+    if (m > 0 && n > 0 && (!d_queries || !d_index || !d_keys)) return fail(NNS_B200_ERR_INVALID, "NULL array");
+    if ((long long)index_base + n > 0x7fffffffLL) return fail(NNS_B200_ERR_INVALID, "index_base + n overflows int32");
+    if (m == 0 || n == 0) return NNS_B200_OK;
+    DeviceCtx* c;
+    ST_TRY(ctx_get(-1, &c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int splits = topk_choose_splits(m, n, c->num_sms);
+    u64* scratch = nullptr;
+    CU_TRY(cudaMallocFromPoolAsync((void**)&scratch, topk_scratch_bytes(m, K, splits), c->pool, st));
+    int launches = 0;
+    const cudaError_t e = topk_search_launch(k, m, n, K, d_queries, d_index + INDEX_HEADER_FLOATS, index_base, (u64*)d_keys, scratch,
+                                             splits, (flags & NNS_B200_FLAG_V0_ROUNDING) != 0, st, &launches);
+    count_launches(launches);
+    const cudaError_t fe = cudaFreeAsync(scratch, st);
+    CU_TRY(e);
+    CU_TRY(fe);
+    return NNS_B200_OK;
+}
+
+int nns_b200_topk_unpack(const uint64_t* d_keys, int m, int K, int* d_idx, float* d_dist, void* stream)
+{
+    if (m < 0 || K < 1 || K > TOPK_MAX_K || (m > 0 && (!d_keys || !d_idx))) return fail(NNS_B200_ERR_INVALID, "invalid keys");
+    CU_TRY(topk_unpack_launch((const u64*)d_keys, m, K, d_idx, d_dist, (cudaStream_t)stream));
+    count_launches(m > 0 ? 1 : 0);
+    return NNS_B200_OK;
+}
+
 size_t nns_b200_workspace_bytes(int k, int m, int n)
 {
     const size_t ib = (nns_b200_index_floats(k, n) * sizeof(float) + 255) & ~(size_t)255;

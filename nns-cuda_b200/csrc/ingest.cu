@@ -187,11 +187,14 @@ void sample_centre_host(int k, int n, const float* r_points, TensorCentre* out)
 // ---------------------------------------------------------------------------------------------
 // Reference chunk of the ingest pipeline, in points.  FP32 paths: ~32 MiB of AoS data.  tcgen05 path:
 // every chunk is searched as an index of its own (own centre, own query image, own candidate seeds),
-// which costs a fixed ~0.2 ms, so chunks are a quarter of the set but at least 24 MiB.
+// which costs a fixed ~0.2 ms, so chunks are a quarter of the set but at least 24 MiB -- and for
+// k > 32 the set is one chunk: every chunk re-scores its own near-minimum candidates exactly, which at
+// k = 128 costs more than the upload it hides (B200, C4: 279 ms in four chunks vs 245 ms in one).
 long long ingest_chunk_points(int k, int n, bool tensor)
 {
     const long long row = (long long)k * 4;
     long long chunk = ((32ll << 20) / row) / LB * LB;
+    if (tensor && k > LOWK_MAX_K) return ((long long)n + LB - 1) / LB * LB > LB ? ((long long)n + LB - 1) / LB * LB : LB;
     if (tensor) {
         const long long quarter = (((long long)n + 3) / 4 + LB - 1) / LB * LB;
         const long long floor24 = ((24ll << 20) / row) / LB * LB;
@@ -443,6 +446,72 @@ int nns_b200_search_host_dist(int k, int m, int n, const float* s_points, const 
     DeviceCtx* c;
     ST_TRY(ctx_get(-1, &c));
     return search_host_on(c, k, m, n, s_points, r_points, 0, nullptr, results, nullptr, distances);
+}
+
+/* K nearest neighbours over host arrays: chunked ingest like nns_b200_search_host, every chunk
+ * accumulating into the same sorted key lists. */
+int nns_b200_search_topk_host(int k, int m, int n, int K, const float* s_points, const float* r_points, int* indices,
+                              float* distances)
+{
+    ST_TRY(check_host_args(k, m, n, s_points, r_points, indices));
+    if (K < 1 || K > TOPK_MAX_K) return fail(NNS_B200_ERR_UNSUPPORTED, "K must be 1..%d", TOPK_MAX_K);
+    if (k > TOPK_MAX_DIMS) return fail(NNS_B200_ERR_UNSUPPORTED, "top-K needs k <= %d", TOPK_MAX_DIMS);
+    if (m == 0) return NNS_B200_OK;
+    DeviceCtx* c;
+    ST_TRY(ctx_get(-1, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard guard;
+    ST_TRY(guard.enter(c->device));
+    const unsigned flags = host_flags();
+    const long long chunk = ingest_chunk_points(k, n, false);
+    const int nchunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
+    const size_t bf = index_block_floats(k);
+    const size_t cells = (size_t)m * K;
+    ST_TRY(buf_reserve(&c->q, (size_t)m * k * sizeof(float)));
+    ST_TRY(buf_reserve(&c->r, (size_t)n * k * sizeof(float)));
+    ST_TRY(buf_reserve(&c->index, ((size_t)INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * bf) * sizeof(float)));
+    ST_TRY(buf_reserve(&c->keys, cells * sizeof(u64)));
+    ST_TRY(buf_reserve(&c->idx, cells * sizeof(int) * 2));
+    ST_TRY(ctx_events(c, nchunks + 1));
+    float* d_q = (float*)c->q.p;
+    float* d_r = (float*)c->r.p;
+    float* d_index = (float*)c->index.p;
+    u64* d_keys = (u64*)c->keys.p;
+    int* d_idx = (int*)c->idx.p;
+    float* d_dist = (float*)(d_idx + cells);
+    ST_TRY(h2d_async(c, d_q, s_points, (size_t)m * k * sizeof(float), c->copy));
+    if (cells > 0x7fffffffLL) return fail(NNS_B200_ERR_INVALID, "m * K too large");
+    CU_TRY(launch_keys_init(d_keys, (int)cells, c->compute));
+    count_launches(2);
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const long long j0 = (long long)ci * chunk;
+        const int cn = (int)((n - j0) < chunk ? (n - j0) : chunk);
+        ST_TRY(h2d_async(c, d_r + j0 * k, r_points + j0 * k, (size_t)cn * k * sizeof(float), c->copy));
+        CU_TRY(cudaEventRecord(c->events[ci], c->copy));
+        CU_TRY(cudaStreamWaitEvent(c->compute, c->events[ci], 0));
+        float* d_blocks_c = d_index + INDEX_HEADER_FLOATS + (j0 / LB) * (long long)bf;
+        CU_TRY(launch_index_build(k, cn, d_r + j0 * k, d_index, d_blocks_c, ci == 0, c->compute));
+        const int splits = topk_choose_splits(m, cn, c->num_sms);
+        u64* scratch = nullptr;
+        CU_TRY(cudaMallocFromPoolAsync((void**)&scratch, topk_scratch_bytes(m, K, splits), c->pool, c->compute));
+        int launches = 0;
+        const cudaError_t e = topk_search_launch(k, m, cn, K, d_q, d_blocks_c, (int)j0, d_keys, scratch, splits,
+                                                 (flags & NNS_B200_FLAG_V0_ROUNDING) != 0, c->compute, &launches);
+        count_launches(launches + 1);
+        const cudaError_t fe = cudaFreeAsync(scratch, c->compute);
+        CU_TRY(e);
+        CU_TRY(fe);
+    }
+    if (nchunks == 0) {
+        CU_TRY(cudaEventRecord(c->events[0], c->copy));
+        CU_TRY(cudaStreamWaitEvent(c->compute, c->events[0], 0));
+    }
+    CU_TRY(topk_unpack_launch(d_keys, m, K, d_idx, distances ? d_dist : nullptr, c->compute));
+    CU_TRY(cudaMemcpyAsync(indices, d_idx, cells * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    if (distances) CU_TRY(cudaMemcpyAsync(distances, d_dist, cells * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+    CU_TRY(cudaStreamSynchronize(c->compute));
+    CU_TRY(cudaStreamSynchronize(c->copy));
+    return NNS_B200_OK;
 }
 
 int nns_b200_sample_centre(int k, int n, const float* r_points, float* centre_out)

@@ -67,6 +67,15 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
                           int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
                           int* launches, unsigned* d_stats, bool tiny_candidate_buffer);
 
+// topk_search.cu -- K nearest neighbours, K <= TOPK_MAX_K (extension; FP32 V0-form distances, any k <= TOPK_MAX_DIMS)
+constexpr int TOPK_MAX_K = 32;
+constexpr int TOPK_MAX_DIMS = 1024;
+int topk_choose_splits(int m, int n, int num_sms);
+size_t topk_scratch_bytes(int m, int K, int splits);
+cudaError_t topk_search_launch(int k, int m, int n, int K, const float* d_queries, const float* d_blocks, int index_base,
+                               u64* d_keys, u64* d_scratch, int splits, bool exact, cudaStream_t st, int* launches);
+cudaError_t topk_unpack_launch(const u64* d_keys, int m, int K, int* d_idx, float* d_dist, cudaStream_t st);
+
 // lowk_inst_N.cu (N = (k-1)/2)
 cudaError_t lowk_launch_range_0(int k, int q, int mode, const LowkArgs& a, int* occ);
 cudaError_t lowk_launch_range_1(int k, int q, int mode, const LowkArgs& a, int* occ);

@@ -75,6 +75,9 @@ lib.nns_b200_workspace_bytes.restype = c_size_t
 lib.nns_b200_search_device.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]
 lib.nns_b200_tensor_stats.argtypes = [POINTER(c_uint)]
 lib.nns_b200_device_sms.argtypes = [c_int]
+lib.nns_b200_topk_keys.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_uint, c_void_p]
+lib.nns_b200_topk_unpack.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+lib.nns_b200_search_topk_host.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
 lib.nns_b200_index_create.argtypes = [c_int, c_int, c_void_p, c_int, POINTER(c_void_p)]
 lib.nns_b200_index_search.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
 lib.nns_b200_index_size.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
@@ -173,6 +176,17 @@ class HostIndex:
             self.close()
         except Exception:
             pass
+
+
+def search_topk_host(k: int, m: int, n: int, K: int, s_points, r_points, return_dist: bool = True):
+    """nns_b200_search_topk_host: (int32[m][K] indices, float32[m][K] squared distances), ascending."""
+    s = _host_f32(s_points, m, k)
+    r = _host_f32(r_points, n, k)
+    idx = np.empty((m, K), dtype=np.int32)
+    dist = np.empty((m, K), dtype=np.float32) if return_dist else None
+    _check(lib.nns_b200_search_topk_host(k, m, n, K, s.ctypes.data, r.ctypes.data, idx.ctypes.data,
+                                         dist.ctypes.data if return_dist else None))
+    return (idx, dist) if return_dist else idx
 
 
 def sample_centre(k: int, n: int, r_points) -> np.ndarray:
@@ -284,6 +298,33 @@ class DeviceIndex:
             _check(lib.nns_b200_search_keys(self.k, m, self.n, queries.data_ptr(), self.index.data_ptr(),
                                             self.index_base, keys.data_ptr(), flags, _stream_ptr(stream)))
         return keys
+
+    def topk_keys(self, queries, K: int, keys=None, flags: int = 0, stream=None):
+        """uint64-as-int64 [m][K] ascending packed keys of the K nearest references (accumulates into
+        `keys` when given: shards / GPUs merge like the 1-NN keys)."""
+        import torch
+
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+        m = queries.shape[0]
+        if keys is None:
+            keys = torch.empty((max(m, 1), K), dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                _check(lib.nns_b200_keys_init(keys.data_ptr(), m * K, _stream_ptr(stream)))
+        with torch.cuda.device(self.device):
+            _check(lib.nns_b200_topk_keys(self.k, m, self.n, K, queries.data_ptr(), self.index.data_ptr(), self.index_base,
+                                          keys.data_ptr(), flags, _stream_ptr(stream)))
+        return keys
+
+    def topk(self, queries, K: int, flags: int = 0, stream=None):
+        import torch
+
+        m = queries.shape[0]
+        keys = self.topk_keys(queries, K, None, flags, stream)
+        idx = torch.empty((max(m, 1), K), dtype=torch.int32, device=self.device)
+        dist = torch.empty((max(m, 1), K), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(lib.nns_b200_topk_unpack(keys.data_ptr(), m, K, idx.data_ptr(), dist.data_ptr(), _stream_ptr(stream)))
+        return idx[:m], dist[:m]
 
     def search(self, queries, flags: int = 0, stream=None, return_dist: bool = False):
         import torch

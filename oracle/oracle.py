@@ -45,6 +45,8 @@ def port():
         lib.oracle_v0_search_omp.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int]
         lib.oracle_v0_search_omp.restype = c_int
         lib.oracle_num_threads.restype = c_int
+        lib.oracle_v0_topk.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        lib.oracle_v0_topk.restype = None
         lib.oracle_set_threads.argtypes = [c_int]
         lib.oracle_set_threads.restype = None
         lib.oracle_check_tie_rule.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, POINTER(c_long)]
@@ -101,6 +103,15 @@ def v0_omp(k, m, n, s, r, chunk: int = 8):
     out = np.zeros(m, dtype=np.int32)
     threads = port().oracle_v0_search_omp(k, m, n, s.ctypes.data, r.ctypes.data, out.ctypes.data, chunk)
     return out, threads
+
+
+def v0_topk(k, m, n, K, s, r):
+    """K nearest neighbours in V0's arithmetic, ordered by (distance, index): (int32[m][K], float32[m][K])."""
+    s, r = _f32(s, m, k), _f32(r, n, k)
+    idx = np.zeros((m, K), dtype=np.int32)
+    dist = np.zeros((m, K), dtype=np.float32)
+    port().oracle_v0_topk(k, m, n, K, s.ctypes.data, r.ctypes.data, idx.ctypes.data, dist.ctypes.data)
+    return idx, dist
 
 
 def ref_v0(k, m, n, s, r) -> np.ndarray:

@@ -82,6 +82,35 @@ int oracle_v0_search_omp(int k, int m, int n, const float *s_points, const float
     return threads;
 }
 
+/* K nearest neighbours: an EXTENSION of the reference (which returns one index, core.cu:52), so there is
+ * nothing in the reference to pin it against beyond K = 1 (tests check K = 1 == V0 wherever a finite
+ * distance exists).  Distances in V0's form and rounding (core.cu:38-43); order = (distance, index)
+ * ascending; NaN / +INF distances are never reported; missing entries are index -1, distance +INF. */
+void oracle_v0_topk(int k, int m, int n, int K, const float *s_points, const float *r_points,
+                    int *out_idx, float *out_dist)
+{
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int i = 0; i < m; ++i) {
+        const float *q = s_points + (size_t)i * (size_t)k;
+        int *bi = out_idx + (size_t)i * (size_t)K;
+        float *bd = out_dist + (size_t)i * (size_t)K;
+        for (int e = 0; e < K; ++e) { bi[e] = -1; bd[e] = INFINITY; }
+        for (int j = 0; j < n; ++j) {
+            const float *r = r_points + (size_t)j * (size_t)k;
+            float acc = 0.0f;
+            for (int t = 0; t < k; ++t) {
+                const float d = q[t] - r[t];
+                acc += d * d;
+            }
+            if (!(acc < INFINITY) || !(acc < bd[K - 1])) continue; /* ascending j: equal distance, higher index loses */
+            int e = K - 1;
+            while (e > 0 && bd[e - 1] > acc) { bd[e] = bd[e - 1]; bi[e] = bi[e - 1]; --e; }
+            bd[e] = acc;
+            bi[e] = j;
+        }
+    }
+}
+
 /* torchrun exports OMP_NUM_THREADS=1; the bench sets the team size it reports explicitly */
 void oracle_set_threads(int n)
 {

@@ -111,3 +111,24 @@ def test_clustered_workload_has_exact_ties(oracle, datagen):
         assert np.array_equal(r[j], q[i])
         same = np.where((r == q[i]).all(axis=1))[0]
         assert j == same.min()
+
+
+def test_topk_oracle_first_neighbour_is_v0_and_lists_are_sorted(oracle):
+    """oracle_v0_topk (extension): K = 1 equals V0; lists are ordered by (distance, index) and agree with
+    a numpy restatement of V0's arithmetic."""
+    from conftest import make_case
+
+    for kind, k, m, n, K in [("grid", 3, 40, 500, 8), ("uniform", 16, 25, 300, 32), ("clustered", 3, 64, 129, 5), ("uniform", 5, 7, 3, 4)]:
+        s, r = make_case(kind, k, m, n, 13)
+        idx, dist = oracle.v0_topk(k, m, n, K, s, r)
+        assert np.array_equal(idx[:, 0], oracle.v0(k, m, n, s, r))
+        for i in range(m):
+            acc = np.zeros(n, dtype=np.float32)
+            for t in range(k):
+                d = (s[i, t] - r[:, t]).astype(np.float32)
+                acc = (acc + (d * d).astype(np.float32)).astype(np.float32)
+            order = np.lexsort((np.arange(n), acc))[:K]
+            kk = min(K, n)
+            assert np.array_equal(idx[i, :kk], order[:kk])
+            assert np.array_equal(dist[i, :kk], acc[order[:kk]])
+            assert np.all(idx[i, kk:] == -1) and np.all(np.isinf(dist[i, kk:]))

@@ -616,3 +616,42 @@ def test_index_parts_and_nccl_gather_world1(nns, oracle, torch_mod):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+# ---- K nearest neighbours (extension) ------------------------------------------
+@pytest.mark.parametrize("kind,k,m,n,K", [("uniform", 3, 1024, 65536, 8), ("grid", 3, 500, 20000, 32), ("clustered", 3, 2000, 1 << 20, 16),
+                                          ("uniform", 16, 300, 50000, 5), ("uniform", 128, 100, 9000, 32), ("uniform", 200, 33, 2000, 3),
+                                          ("uniform", 3, 50, 20, 32), ("uniform", 3, 5, 0, 4), ("grid", 2, 1, 300000, 1)])
+def test_topk_matches_the_v0_form_oracle(nns, oracle, torch_mod, kind, k, m, n, K):
+    """nns_b200_topk_keys / nns_b200_search_topk_host: the K nearest references by (V0-form FP32 distance, index)
+    must equal the oracle exactly with NNS_B200_FLAG_V0_ROUNDING (duplicates, grids, n < K, n = 0 included),
+    and K = 1 must be V0's answer."""
+    torch = torch_mod
+    s, r = make_case(kind, k, m, max(n, 1), 61)
+    r = r[:n]
+    want_i, want_d = oracle.v0_topk(k, m, n, K, s, r)
+    if n > 0:
+        index = nns.DeviceIndex(dev(torch, r))
+        gi, gd = index.topk(dev(torch, s), K, nns.FLAG_V0_ROUNDING)
+        gi, gd = gi.cpu().numpy(), gd.cpu().numpy()
+        assert np.array_equal(gi, want_i), int((gi != want_i).sum())
+        assert np.array_equal(gd, want_d)
+        # two reference shards accumulate into the same lists
+        h = (n // 2 + 127) // 128 * 128
+        if 0 < h < n:
+            keys = None
+            for r0, r1 in ((h, n), (0, h)):
+                part = nns.DeviceIndex(dev(torch, r[r0:r1]), index_base=r0)
+                keys = part.topk_keys(dev(torch, s), K, keys, nns.FLAG_V0_ROUNDING)
+            assert np.array_equal((keys.cpu().numpy().astype(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)[want_i >= 0], want_i[want_i >= 0])
+    # host ABI (default FMA rounding): same sets up to FP32 rounding of near-ties -- on grids identical
+    hi, hd = nns.search_topk_host(k, m, n, K, s, r)
+    if kind != "uniform":
+        assert np.array_equal(hi, want_i)
+    else:
+        assert (hi != want_i).mean() < 0.01
+    np.testing.assert_allclose(hd[want_i >= 0], want_d[want_i >= 0], rtol=2e-6)
+    assert np.all(hi[want_i < 0] == -1)
+    if n > 0 and kind != "uniform":
+        v, _ = oracle.v0_omp(k, m, n, s, r)
+        assert np.array_equal(hi[:, 0], v)
