@@ -65,6 +65,9 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #ifndef NNS_T_SPIN
 #define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
 #endif
+#ifndef NNS_T_TS
+#define NNS_T_TS 1          // 1 = contractions of 64 columns and more keep the A operand in tensor memory
+#endif
 #ifndef NNS_T_EXPERIMENT
 #define NNS_T_EXPERIMENT 0  // timing experiments only (wrong results): 1 = epilogue reduces 2 of 32 columns,
 #endif                      // 2 = epilogue does not read TMEM at all, 3 = additionally no MMA is issued
@@ -115,6 +118,25 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, u64 adesc, u64 bdes
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the A operand in tensor memory (lane = row, 8 columns = 16 bf16 of one K step): only B is
+// fetched from shared memory, half the operand traffic of the shared-memory form
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u64 bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> tensor memory: each thread writes 8 consecutive columns of its own lane
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 lo, const uint4 hi)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -471,7 +493,13 @@ __device__ __forceinline__ void cand_emit(const CandBuf& cb, unsigned* s_count, 
 // SUB = 1 build at k = 3).  Only for KB = 0: an N = 64 MMA re-reads the A operand twice as often, and
 // at M = 128 the shared-memory operand fetch already runs at its 128 B/clk limit when the tensor
 // pipe is the bound (k >= 10).
-template <int KB, int KS, int T_STAGES, int G, int SUB>
+// TS = the A operand (the strip's query image) lives in TENSOR MEMORY instead of shared memory: the
+// epilogue warps of team 0 copy it there once (tcgen05.st), and every MMA then fetches only B from shared
+// memory.  At M = 128 the shared-memory operand fetch of the SS form runs at its 128 B/clk limit, which is
+// what ruled out N = 64 units (A re-read twice as often) for the longer contractions; with A in TMEM the
+// units can be 64 references wide and NBUF = 3 accumulator buffers fit beside A (2 * 3 * 64 + A columns
+// <= 512), so an epilogue team has two unit periods to drain a buffer instead of one.
+template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS>
 __global__ void __maxnreg__(T_MAX_REGS)
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
@@ -482,15 +510,19 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     constexpr uint32_t A_BYTES = (uint32_t)image_bytes(T_BM, KB, KS);  // 72 KiB at KB = 2, KS = 1
     constexpr uint32_t B_BYTES = (uint32_t)image_bytes(T_BN, KB, KS);  // 36 KiB at KB = 2, KS = 1
     constexpr uint32_t STAGE_BYTES = G * B_BYTES;
-    constexpr int NBUF = 2 * SUB;              // TMEM accumulator buffers
     constexpr int SN = T_BN / SUB;             // references (TMEM columns) per accumulator unit
+    constexpr int STEPS = KB * 4 + KS;         // K = 16 MMA steps per unit and accumulator half
+    constexpr uint32_t A_COL0 = 2 * NBUF * SN; // TS: first TMEM column of the A operand, [half][step][8 columns]
+    static_assert(!TS || A_COL0 + 2 * STEPS * 8 <= 512, "accumulators + A operand exceed the 512 TMEM columns");
+    static_assert(TS || 2 * NBUF * SN <= 512, "accumulators exceed the 512 TMEM columns");
+    constexpr uint32_t A_SMEM = TS ? 0u : A_BYTES;
     constexpr int CPU = SN / 32;               // 32-column chunks per unit
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N = SN, M = 128
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_smem = smem;
-    unsigned char* b_smem = smem + A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + T_STAGES * STAGE_BYTES);
+    unsigned char* b_smem = smem + A_SMEM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_SMEM + T_STAGES * STAGE_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_MAX_STAGES + 8);
     unsigned* s_cand_count = tmem_slot + 1;
     const uint32_t bar0 = smem_u32(bars);
@@ -516,7 +548,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < T_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
         for (int i = 0; i < NBUF; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_TEAM_WARPS); }
-        mbar_init(a_full, 1);
+        mbar_init(a_full, TS ? T_TEAM_WARPS : 1);
         mbar_fence_init();
         *s_cand_count = 0;
     }
@@ -529,8 +561,10 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     if (warp == 0) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            mbar_arrive_expect_tx(a_full, A_BYTES);
-            bulk_g2s(smem_u32(a_smem), qimage + (size_t)blockIdx.x * A_BYTES, A_BYTES, a_full);
+            if (!TS) {
+                mbar_arrive_expect_tx(a_full, A_BYTES);
+                bulk_g2s(smem_u32(a_smem), qimage + (size_t)blockIdx.x * A_BYTES, A_BYTES, a_full);
+            }
             int s = 0;
             uint32_t ph = 0;
             for (int g0 = 0; g0 < nt; g0 += G) {
@@ -554,6 +588,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         // TMEM buffers so that buffer addresses and barrier addresses are immediates.
         if (elect_one_sync()) {
             mbar_wait(a_full, 0);
+            tc_fence_after();
             const uint32_t a_addr = smem_u32(a_smem), b_addr0 = smem_u32(b_smem);
             u64 adesc_sw[KB > 0 ? KB : 1][4][2], adesc_il[KS > 0 ? KS : 1][2];
             uint32_t bdesc_sw_lo[KB > 0 ? KB : 1][4], bdesc_il_lo[KS > 0 ? KS : 1];
@@ -592,15 +627,21 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     for (int ks = 0; ks < 4; ++ks) {
                         const u64 bdesc = ((u64)bdesc_sw_hi << 32) | (u64)(bdesc_sw_lo[kb][ks] + sw16);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_sw[kb][ks][h], bdesc, IDESC, (uint32_t)((kb | ks) != 0));
+                        for (int h = 0; h < 2; ++h) {
+                            if (NNS_T_EXPERIMENT >= 3) continue;
+                            if (TS) tc_mma_bf16_ts(tmem_base + (uint32_t)((buf * 2 + h) * SN), tmem_base + A_COL0 + (uint32_t)((h * STEPS + kb * 4 + ks) * 8), bdesc, IDESC, (uint32_t)((kb | ks) != 0));
+                            else tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_sw[kb][ks][h], bdesc, IDESC, (uint32_t)((kb | ks) != 0));
+                        }
                     }
 #pragma unroll
                 for (int x = 0; x < KS; ++x) {  // interleaved steps (the last columns carry |r'|^2)
                     const u64 bdesc = ((u64)bdesc_il_hi << 32) | (u64)(bdesc_il_lo[x] + il16);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        if (NNS_T_EXPERIMENT < 3) tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_il[x][h], bdesc, IDESC, (uint32_t)((KB | x) != 0));
+                    for (int h = 0; h < 2; ++h) {
+                        if (NNS_T_EXPERIMENT >= 3) continue;
+                        if (TS) tc_mma_bf16_ts(tmem_base + (uint32_t)((buf * 2 + h) * SN), tmem_base + A_COL0 + (uint32_t)((h * STEPS + KB * 4 + x) * 8), bdesc, IDESC, (uint32_t)((KB | x) != 0));
+                        else tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_il[x][h], bdesc, IDESC, (uint32_t)((KB | x) != 0));
+                    }
                 }
                 tc_commit(acc_full + 8 * buf);   // accumulator complete
                 T_TRACE(3, u);
@@ -620,7 +661,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             for (int u = 0; u < nt * SUB; u += NBUF) {
 #pragma unroll
                 for (int i = 0; i < NBUF; ++i)
-                    if (u + i < nt * SUB) issue_unit(u + i, i, i % SUB);
+                    if (u + i < nt * SUB) issue_unit(u + i, i, (NBUF % SUB == 0) ? i % SUB : (u + i) % SUB);
             }
         }
     } else {
@@ -640,6 +681,21 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         float run_min = (q < m) ? ord2f(approx_min[q]) : inf_f();
         float thresh = run_min + my_band;
         const uint32_t lane_base = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * SN);
+        if (TS && team == 0) {
+            // this thread's row of the query image -> its TMEM lane, 8 columns (two 16-byte chunks) per K step
+            const unsigned char* qrow = qimage + (size_t)blockIdx.x * A_BYTES;
+            const uint32_t a_lane = tmem_base + ((uint32_t)(lq * 32) << 16) + A_COL0 + (uint32_t)(half * STEPS * 8);
+#pragma unroll
+            for (int st = 0; st < STEPS; ++st) {
+                const uint4 lo = __ldg(reinterpret_cast<const uint4*>(qrow + image_chunk_at(T_BM, KB, row, 2 * st)));
+                const uint4 hi = __ldg(reinterpret_cast<const uint4*>(qrow + image_chunk_at(T_BM, KB, row, 2 * st + 1)));
+                tmem_st8(a_lane + (uint32_t)(st * 8), lo, hi);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         // One TMEM chunk in flight per warp: with four epilogue warps per scheduler the load latency
         // of one warp is covered by the reductions of the other three.  (A register double buffer
         // measured no faster at k = 3 and slower at k = 128, where the box runs at its power cap.)
@@ -881,22 +937,29 @@ cudaError_t tensor_index_build(int k, int n, const float* d_blocks, float* d_sec
 
 // reference tiles per TMA stage / ring depth per operand geometry (stage = G tiles <= 36 KiB)
 static int tensor_group(const TensorGeom& g) { return g.KB == 0 ? (g.KS == 1 ? 4 : 2) : 1; }
-static int tensor_stages(const TensorGeom& g) { return g.KB == 2 ? 4 : g.KB == 1 ? (g.KS == 0 ? 8 : 6) : 6; }
+// must match the STAGES arguments of the NNS_SCREEN table in tensor_search()
+static int tensor_stages(const TensorGeom& g)
+{
+    if (g.KB == 0) return 6;
+    if (NNS_T_TS) return g.KB == 2 ? 5 : 8;
+    return g.KB == 2 ? 4 : (g.KS == 0 ? 8 : 6);
+}
 
 static size_t tensor_smem_bytes(const TensorGeom& g)
 {
-    return image_bytes(T_BM, g.KB, g.KS) + (size_t)tensor_stages(g) * tensor_group(g) * image_bytes(T_BN, g.KB, g.KS) +
+    const bool ts = NNS_T_TS && g.KB > 0;  // A lives in TMEM: no shared-memory A tile
+    return (ts ? 0 : image_bytes(T_BM, g.KB, g.KS)) + (size_t)tensor_stages(g) * tensor_group(g) * image_bytes(T_BN, g.KB, g.KS) +
            (2 * T_MAX_STAGES + 8) * 8 + 16;
 }
 
-template <int KB, int KS, int STAGES, int G, int SUB>
+template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS>
 static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
                                         const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
                                         const CandBuf& cb)
 {
-    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_screen_kernel<KB, KS, STAGES, G, SUB><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb);
+    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb);
     return cudaGetLastError();
 }
 
@@ -1034,14 +1097,23 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
         dim3 grid((unsigned)bs, (unsigned)splits);
-#define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_) \
-    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_>(grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb)
-        if (g.KB == 0 && g.KS == 1) e = NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB);
-        else if (g.KB == 0) e = NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB);
-        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1, 1);
-        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 6, 1, 1);
-        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 4, 1, 1);
-        else e = NNS_SCREEN(2, 1, 4, 1, 1);
+#define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_, NBUF_, TS_) \
+    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_>(grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb)
+        // short contractions (k <= 9): SS form, 4 buffers of 64 references; longer ones: A in TMEM (NNS_T_TS),
+        // 64-reference units in 3 buffers (2 where A needs more than 128 columns)
+        if (g.KB == 0 && g.KS == 1) e = NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false);
+        else if (g.KB == 0) e = NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false);
+#if NNS_T_TS
+        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1, 2, 3, true);
+        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 8, 1, 2, 3, true);
+        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 5, 1, 2, 3, true);
+        else e = NNS_SCREEN(2, 1, 5, 1, 2, 2, true);
+#else
+        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1, 1, 2, false);
+        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 6, 1, 1, 2, false);
+        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 4, 1, 1, 2, false);
+        else e = NNS_SCREEN(2, 1, 4, 1, 1, 2, false);
+#endif
 #undef NNS_SCREEN
         if (e != cudaSuccess) break;
         const int rgrid = num_sms * 8;

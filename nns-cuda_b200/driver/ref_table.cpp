@@ -4,10 +4,19 @@
 // Its output lines can be diffed against the reference's `./main` (profiles/r1_ref_main_b200.txt).
 // This is SURVEY.md section 8(f) row n1; it is a caller of the hot path, not part of it.
 //
+//
+//   ref_table [reps] [dump_dir]
+// Like the reference -- whose static WarmUP creates the CUDA context and runs ten small searches before
+// main() (core.cu:1900-1933) -- the driver warms up before the table: nns_b200_init + one small call, so
+// that the first line does not time context creation.  With dump_dir, the indices of every line of
+// the first repetition are written to dump_dir/results_<line>.bin; tests/test_ref_table.py checks them
+// against the V0 oracle on the same generator stream (the reference's driver never inspects a result).
+//
 //   g++ -O2 -I../../include -I../shim ref_table.cpp -L../lib -lnns_b200 -Wl,-rpath,'$ORIGIN/../lib' -o ref_table
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
+#include <string>
 
 #include "nns_b200.hpp"
 
@@ -40,7 +49,16 @@ int main(int argc, char **argv)
 {
     const int version = 14;  // the reference's own variants are 0..13 (main.cu:87-135)
     const int reps = argc > 1 ? atoi(argv[1]) : 1;
+    const char *dump_dir = argc > 2 ? argv[2] : nullptr;
     func = &b200::cudaCall;
+    {   // the counterpart of the reference's load-time WarmUP (core.cu:1923-1928: k = 1, m = 1, n = 32768)
+        nns_b200_init(-1);
+        float q = 0.5f, *r = (float *)calloc(32768, sizeof(float));
+        int *res = nullptr;
+        (*func)(1, 1, 32768, &q, r, &res);
+        free(res);
+        free(r);
+    }
     const int total = (int)(sizeof(samples) / (3 * sizeof(*samples)));
     printf("\nRunning CUDACALL %d...\n", version);  // main.cu:136
     for (int rep = 0; rep < reps; ++rep) {
@@ -54,6 +72,14 @@ int main(int argc, char **argv)
             (*func)(k, m, n, s_points, r_points, &results);
             const long et = get_time_ns();
             printf("CudaCall %d, %2d, %4d, %10d, %10.3fms\n", version, k, m, n, (et - st) / 1e6);  // main.cu:76
+            if (dump_dir && rep == 0) {
+                const std::string path = std::string(dump_dir) + "/results_" + std::to_string(i) + ".bin";
+                FILE *f = fopen(path.c_str(), "wb");
+                if (f) {
+                    fwrite(results, sizeof(int), (size_t)m, f);
+                    fclose(f);
+                }
+            }
             free(results);  // the reference's driver leaks this (main.cu:72-78)
             free(s_points);
             free(r_points);

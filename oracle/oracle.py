@@ -45,6 +45,8 @@ def port():
         lib.oracle_v0_search_omp.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int]
         lib.oracle_v0_search_omp.restype = c_int
         lib.oracle_num_threads.restype = c_int
+        lib.oracle_libc_rand_fill.argtypes = [c_void_p, c_long]
+        lib.oracle_libc_rand_fill.restype = None
         lib.oracle_v0_topk.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         lib.oracle_v0_topk.restype = None
         lib.oracle_set_threads.argtypes = [c_int]
@@ -103,6 +105,19 @@ def v0_omp(k, m, n, s, r, chunk: int = 8):
     out = np.zeros(m, dtype=np.int32)
     threads = port().oracle_v0_search_omp(k, m, n, s.ctypes.data, r.ctypes.data, out.ctypes.data, chunk)
     return out, threads
+
+
+def reference_table_inputs(shapes, seed: int = 1000):
+    """Inputs of the reference's benchmark table (main.cu:54, 62-71): srand(seed) once, then for every
+    (k, m, n) the queries followed by the references from the same libc stream.  Yields (k, m, n, s, r)."""
+    libc = ctypes.CDLL(None)
+    libc.srand(ctypes.c_uint(seed))
+    for (k, m, n) in shapes:
+        s = np.empty((m, k), dtype=np.float32)
+        r = np.empty((n, k), dtype=np.float32)
+        port().oracle_libc_rand_fill(s.ctypes.data, m * k)
+        port().oracle_libc_rand_fill(r.ctypes.data, n * k)
+        yield k, m, n, s, r
 
 
 def v0_topk(k, m, n, K, s, r):

@@ -111,6 +111,14 @@ void oracle_v0_topk(int k, int m, int n, int K, const float *s_points, const flo
     }
 }
 
+/* The reference's generator stream (main.cu:10-13): count values of rand() / double(RAND_MAX) from the
+ * process-wide libc generator, continuing wherever srand()/rand() left it.  Lets tests reproduce the
+ * inputs of the reference's whole shape table (one srand(1000), ten shapes in sequence) quickly. */
+void oracle_libc_rand_fill(float *dst, long count)
+{
+    for (long i = 0; i < count; ++i) dst[i] = (float)(rand() / (double)RAND_MAX);
+}
+
 /* torchrun exports OMP_NUM_THREADS=1; the bench sets the team size it reports explicitly */
 void oracle_set_threads(int n)
 {

@@ -2,23 +2,23 @@
 # tools/tensor_tune.sh build | run -- kernel-variant sweep of the tcgen05 screen (csrc/tensor_search.cu).
 #   build : compile one libnns_b200_<name>.so per variant into nns-cuda_b200/lib/exp/ (no GPU needed)
 #   run   : on a B200, bench every variant on the workloads in $WORKLOADS and print one line each
-# Variants are "name:TEAMS:SPIN[:EXPERIMENT]".
+# Variants are "name:DEF=VAL,DEF=VAL..." (the NNS_T_* knobs at the top of tensor_search.cu).
 set -e
 cd "$(dirname "$0")/../nns-cuda_b200"
-VARIANTS=${VARIANTS:-"t2s0:2:0 t2s1:2:1 t1s0:1:0"}
+VARIANTS=${VARIANTS:-"ts1:NNS_T_TS=1 ts0:NNS_T_TS=0"}
 WORKLOADS=${WORKLOADS:-"c2 c3 c4"}
 if [ "$1" = build ]; then
     make >/dev/null
     mkdir -p build/exp lib/exp
     for v in $VARIANTS; do
-        IFS=: read name teams spin xp <<<"$v"
+        name=${v%%:*}; defs=${v#*:}
+        dflags=$(echo "$defs" | tr ',' '\n' | sed 's/^/-D/' | tr '\n' ' ')
         nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 \
-            -DNNS_T_TEAMS=$teams -DNNS_T_SPIN=$spin -DNNS_T_EXPERIMENT=${xp:-0} $EXTRA_DEFS \
-            -c -o build/exp/tensor_search_$name.o csrc/tensor_search.cu &
+            $dflags $EXTRA_DEFS -c -o build/exp/tensor_search_$name.o csrc/tensor_search.cu &
     done
     wait
     for v in $VARIANTS; do
-        IFS=: read name teams spin xp <<<"$v"
+        name=${v%%:*}
         objs=$(ls build/*.o | grep -v tensor_search.o)
         nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/exp/libnns_b200_$name.so $objs build/exp/tensor_search_$name.o -lpthread
     done
@@ -26,15 +26,15 @@ if [ "$1" = build ]; then
 else
     cd ..
     for v in $VARIANTS; do
-        IFS=: read name teams spin xp <<<"$v"
+        name=${v%%:*}
         for wl in $WORKLOADS; do
-            NNS_B200_LIB=$PWD/nns-cuda_b200/lib/exp/libnns_b200_$name.so python bench.py --workload $wl --flags 8 --steps 3 \
-                --no-cpu-baseline --no-e2e 2>&1 | python -c "
+            NNS_B200_LIB=$PWD/nns-cuda_b200/lib/exp/libnns_b200_$name.so python bench.py --workload $wl --flags 8 --steps ${STEPS:-3} \
+                --no-cpu-baseline --no-e2e --also none 2>&1 | python -c "
 import sys, json
 line = sys.stdin.read().strip().splitlines()[-1]
 try:
     d = json.loads(line)
-    print('$name $wl %.3e pairs/s %.3f ms sm_mhz=%s %s' % (d['value'], d['ms_per_step'], d['clocks'].get('sm_mhz'), d['clocks'].get('reasons')))
+    print('$name $wl %.3e pairs/s %.3f ms sm_mhz=%s %s cand=%s' % (d['value'], d['ms_per_step'], d['clocks'].get('sm_mhz'), d['clocks'].get('reasons'), d['roofline'].get('tensor_stats')))
 except Exception as e:
     print('$name $wl FAILED', line[-300:])
 "
