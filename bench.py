@@ -287,11 +287,12 @@ def roofline_of(nns_b200, name, k, m, nloc, flags, kern_ms_avg, clocks, world, t
         # (ONE minimum per pair in the TMEM epilogue: priced by executed lane-slots) and the tensor
         # pipe (algorithmic 2k FLOPs per pair; the hi/lo column triples and padding are real MMA work but
         # count as zero -- `tensor_frac_executed` shows them).  `bound` = the one with the higher utilisation.
-        kp = nns_b200.tensor_kp(k)
+        kp = (tstats or {}).get("kp") or nns_b200.tensor_kp(k)  # the precision mode the index chose (split or plain BF16 columns)
         alu_frac = rate * 1.0 / lane_peak
         tensor_frac = rate * 2.0 * k / 1e12 / bf16_peak
         tensor_exec = rate * 2.0 * kp / 1e12 / bf16_peak
-        kernel = "tcgen05 split-precision BF16 screen (K = %d columns for k = %d) + query image + exact FP32 re-score" % (kp, k)
+        kernel = "tcgen05 %s BF16 screen (K = %d columns for k = %d) + query image + exact FP32 re-score" % (
+            "split-precision" if kp >= 3 * k else "plain", kp, k)
         if alu_frac >= tensor_exec:
             roofline = {"bound": "fp32", "achieved": rate * 2.0 / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": alu_frac,
                         "kernel": kernel + "; bound by one FMNMX3 lane-slot per pair in the TMEM epilogue",

@@ -181,9 +181,10 @@ int nns_b200_search_device(int k, int m, int n, const float *d_queries, const fl
 int nns_b200_plan(int k, int m, int n, unsigned flags, int num_sms, int *plan);
 
 /* diagnostics of the last tensor-path search on the current device (synchronises the device):
- * out3 = { (query, 32-reference unit) candidates emitted by the tcgen05 screen, 1 if the candidate
- * buffer overflowed and the FP32 kernel launched behind it redid the search, candidate capacity } */
-int nns_b200_tensor_stats(unsigned *out3);
+ * out4 = { (query, 32-reference unit) candidates emitted by the tcgen05 screen, 1 if the candidate
+ * buffer overflowed and the FP32 kernel launched behind it redid the search, candidate capacity of a
+ * query batch, contraction length (BF16 columns) of the operand images the index chose } */
+int nns_b200_tensor_stats(unsigned *out4);
 
 /* number of kernels of this library launched by this process so far (bench.py's gpu_launches) */
 unsigned long long nns_b200_launch_count(void);

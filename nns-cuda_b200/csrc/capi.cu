@@ -368,7 +368,7 @@ int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, co
                 te = wide_launch(mode == LOWK_EXACT_V0, a);
             }
             // keep the last search's status words for nns_b200_tensor_stats()
-            if (te == cudaSuccess) te = cudaMemcpyAsync(c->stats.p, d_status, 3 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+            if (te == cudaSuccess) te = cudaMemcpyAsync(c->stats.p, d_status, 4 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
         }
         const cudaError_t fe = cudaFreeAsync(d_status, st);
         ST_TRY(fst);
@@ -498,7 +498,7 @@ int nns_b200_index_build(int k, int n, const float* d_refs_aos, float* d_index, 
     if (n == 0) return NNS_B200_OK;
     float* d_blocks = d_index + INDEX_HEADER_FLOATS;
     CU_TRY(launch_index_build(k, n, d_refs_aos, d_index, d_blocks, true, (cudaStream_t)stream));
-    CU_TRY(tensor_index_build(k, n, d_blocks, section_of(k, n, d_index), (cudaStream_t)stream));
+    CU_TRY(tensor_index_build(k, n, d_index, d_blocks, section_of(k, n, d_index), (cudaStream_t)stream));
     count_launches(tensor_section_floats(k, n) ? 4 : 1);
     return NNS_B200_OK;
 }
@@ -657,7 +657,7 @@ int nns_b200_search_device(int k, int m, int n, const float* d_queries, const fl
     float* d_section = nullptr;
     if (plan_wants_tensor(k, m, n, flags, c->num_sms)) {
         d_section = section_of(k, n, d_index);
-        CU_TRY(tensor_index_build(k, n, d_blocks, d_section, st));
+        CU_TRY(tensor_index_build(k, n, d_index, d_blocks, d_section, st));
     }
     count_launches(n > 0 ? 3 : 2);  // + the unpack below
     ST_TRY(search_keys_on(c, k, m, n, d_queries, d_index, d_blocks, d_section, 0, d_keys, flags, st));
@@ -665,16 +665,17 @@ int nns_b200_search_device(int k, int m, int n, const float* d_queries, const fl
     return NNS_B200_OK;
 }
 
-int nns_b200_tensor_stats(unsigned* out3)
+int nns_b200_tensor_stats(unsigned* out4)
 {
+    unsigned* out3 = out4;
     if (!out3) return fail(NNS_B200_ERR_INVALID, "NULL out");
     DeviceCtx* c;
     ST_TRY(ctx_get(-1, &c));
     std::lock_guard<std::mutex> lk(c->mu);
-    out3[0] = out3[1] = out3[2] = 0;
+    out3[0] = out3[1] = out3[2] = out3[3] = 0;
     if (!c->stats.p) return NNS_B200_OK;
     CU_TRY(cudaDeviceSynchronize());
-    CU_TRY(cudaMemcpy(out3, c->stats.p, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(out3, c->stats.p, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost));
     return NNS_B200_OK;
 }
 

@@ -258,7 +258,7 @@ int search_host_locked(DeviceCtx* c, int k, int m, int n, const float* s, const 
         float* d_section_c = nullptr;
         if (tensor) {
             d_section_c = (float*)c->tsec.p + (size_t)ci * chunk_sec_floats;
-            CU_TRY(tensor_index_build(k, cn, d_blocks_c, d_section_c, c->compute));
+            CU_TRY(tensor_index_build(k, cn, d_index, d_blocks_c, d_section_c, c->compute));
             count_launches(3);
         }
         ST_TRY(search_keys_on(c, k, m, cn, d_q, d_index, d_blocks_c, d_section_c, index_base + (int)j0, d_keys, flags,
@@ -386,7 +386,7 @@ int nns_b200_index_search(nns_b200_index_t* h, int m, const float* s_points, int
     // the tensor section is added to the index by the first search that is planned onto tcgen05
     if (!h->has_section && plan_wants_tensor(k, m, n, flags, c->num_sms)) {
         if (!h->d_section) CU_TRY(cudaMalloc((void**)&h->d_section, tensor_section_floats(k, n) * sizeof(float)));
-        CU_TRY(tensor_index_build(k, n, h->d_index + INDEX_HEADER_FLOATS, h->d_section, c->compute));
+        CU_TRY(tensor_index_build(k, n, h->d_index, h->d_index + INDEX_HEADER_FLOATS, h->d_section, c->compute));
         h->has_section = true;
         count_launches(3);
     }

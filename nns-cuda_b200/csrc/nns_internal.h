@@ -12,7 +12,8 @@ namespace nns {
 // [THDR_FLAGS] bit 0: unusable; [THDR_PART_MAX + g], [THDR_PART_FLAGS + g] per-GPU partials (multi-GPU ingest)
 constexpr int MAX_PEERS = 8;
 constexpr int HDR_PART_MAX = 8;
-constexpr int THDR_MAX = 128, THDR_FLAGS = 129, THDR_PART_MAX = 136, THDR_PART_FLAGS = 152;
+constexpr int THDR_MAX = 128, THDR_FLAGS = 129, THDR_MODE = 131, THDR_PART_MAX = 136, THDR_PART_FLAGS = 152;
+// [THDR_MODE] 0 = split-precision operand images, 1 = plain BF16 (only for TENSOR_PLAIN_MIN_K <= k <= TENSOR_SPLIT_MAX_K)
 struct BlockDsts { float* p[MAX_PEERS]; int count; };            // first block of the part in every destination index
 struct ImageDsts { unsigned char* p[MAX_PEERS]; int count; };    // first tile image of the part in every destination
 struct HeaderPeers { float* header[MAX_PEERS]; float* section[MAX_PEERS]; int count; int self; };
@@ -48,7 +49,11 @@ cudaError_t wide_launch(bool exact, const WideArgs& a);
 
 // tensor_search.cu -- tcgen05 path for k <= TENSOR_MAX_K (split-precision BF16 up to TENSOR_SPLIT_MAX_K)
 constexpr int TENSOR_MAX_K = 128;
-constexpr int TENSOR_SPLIT_MAX_K = 42;  // 3k <= 128 contraction columns
+#ifndef NNS_T_SPLIT_MAX
+#define NNS_T_SPLIT_MAX 42
+#endif
+constexpr int TENSOR_SPLIT_MAX_K = NNS_T_SPLIT_MAX;  // 3k <= 128 contraction columns
+constexpr int TENSOR_PLAIN_MIN_K = 10;  // below, the plain band is never selective enough (k = 3: 2E = 6e-3 vs d^2 ~ 4e-5)
 constexpr int TENSOR_HDR_FLOATS = 256;  // [0..127] centre, [128] max |r'|^2 bits, [129] flags
 int tensor_kp(int k);
 size_t tensor_section_floats(int k, int n);
@@ -61,7 +66,9 @@ cudaError_t tensor_section_init(int k, int n, const float* d_blocks, float* d_se
 cudaError_t tensor_image_build(int k, int cn, const float* d_blocks_part, float* d_hdr, int max_word, int flag_word,
                                const ImageDsts& dst, cudaStream_t st, int write_blocks = 0);
 // section_init (sampled centre) + image_build of the whole index
-cudaError_t tensor_index_build(int k, int n, const float* d_blocks, float* d_section, cudaStream_t st);
+// d_header: the FP32 index header (max |r|^2 feeds the precision-mode probe); NULL = no probe, split layout
+cudaError_t tensor_index_build(int k, int n, const float* d_header, const float* d_blocks, float* d_section, cudaStream_t st);
+bool tensor_has_modes(int k);
 // scratch comes from `pool` (stream-ordered); *launches = kernels launched
 cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
                           int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,

@@ -241,10 +241,11 @@ __device__ __forceinline__ size_t image_chunk_offset(int rows, int row, int kb, 
 struct TensorGeom {
     int KB, KS, norm_col, ndata, split;
 };
-__host__ __device__ inline TensorGeom tensor_geom(int k)
+// plain = single BF16 column per dimension even where the split-precision layout exists (see "Precision mode")
+__host__ __device__ inline TensorGeom tensor_geom(int k, bool plain = false)
 {
     TensorGeom g;
-    g.split = k <= TENSOR_SPLIT_MAX_K ? 1 : 0;
+    g.split = (k <= TENSOR_SPLIT_MAX_K && !plain) ? 1 : 0;
     g.ndata = g.split ? 3 * k : k;
     // the three norm columns ride in the last block whenever it has room for them
     if (g.ndata + 3 <= 16) { g.KB = 0; g.KS = 1; g.norm_col = g.ndata; }
@@ -269,12 +270,24 @@ __device__ __forceinline__ size_t image_chunk_at(int rows, int KB, int row, int 
 // makes one BF16 MMA pass accumulate qh.rh + qh.rl + ql.rh, i.e. q'.r' up to terms of relative size
 // ~3 * 2^-18: the screen's error bound E shrinks ~250x, so that it is selective even for k = 3 with
 // millions of references (nearest-neighbour distances ~1e-5 of the data extent).
-__host__ __device__ constexpr bool tensor_split(int k) { return k <= TENSOR_SPLIT_MAX_K; }
+//
+// Precision mode.  For TENSOR_PLAIN_MIN_K <= k <= TENSOR_SPLIT_MAX_K both layouts exist: split columns
+// (contraction 3k + 3) or plain BF16 (k + 3, a third of the tensor work; E ~250x larger).  Which one is
+// cheaper depends on the data: the screen stays selective as long as the band 2E is small against the
+// nearest-neighbour distances (uniform k = 16, n = 16.7 M: 2E = 0.03 vs d^2 = 0.16 -> 3 references inside
+// the band), but on data of low intrinsic dimension the plain band holds thousands.  tensor_index_build
+// decides per index with a probe (tensor_mode_kernel) and leaves the choice in the section header
+// (THDR_MODE); every kernel of the path is launched in both variants and the one that does not match the
+// header word exits at once -- no host round trip.
+__device__ __forceinline__ bool tensor_mode_mismatch(const unsigned* __restrict__ mode_word, const unsigned my_mode)
+{
+    return mode_word != nullptr && *reinterpret_cast<const volatile unsigned*>(mode_word) != my_mode;
+}
 // source dimension and part (0 = hi, 1 = lo) of data column `col` (< ndata); dimension -1 = none
-__device__ __forceinline__ void image_column(int k, int ndata, int col, bool query, int& dim, int& part)
+__device__ __forceinline__ void image_column(int k, int ndata, bool split, int col, bool query, int& dim, int& part)
 {
     if (col >= ndata) { dim = -1; part = 0; return; }
-    if (!tensor_split(k)) { dim = col; part = 0; return; }
+    if (!split) { dim = col; part = 0; return; }
     const int seg = col / k;
     dim = col - seg * k;
     part = query ? (seg == 2 ? 1 : 0) : (seg == 1 ? 1 : 0);
@@ -341,8 +354,10 @@ __global__ void tensor_centre_kernel(float* __restrict__ hdr, const int k, const
 // Like index_build_kernel it can store to the same slice of several peer GPUs' sections.
 __global__ void __launch_bounds__(128)
 tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int k, const TensorGeom g,
-                        float* __restrict__ hdr, const int max_word, const int flag_word, const ImageDsts dst)
+                        float* __restrict__ hdr, const int max_word, const int flag_word, const ImageDsts dst,
+                        const unsigned* __restrict__ mode_word, const unsigned my_mode)
 {
+    if (tensor_mode_mismatch(mode_word, my_mode)) return;
     const long long b = blockIdx.x;
     const int row = threadIdx.x;  // one thread per reference
     const long long j = b * T_BN + row;
@@ -374,7 +389,7 @@ tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int
         for (int e = 0; e < 8; ++e) {
             const int c = ch * 8 + e;
             int dim, part;
-            image_column(k, g.ndata, c, false, dim, part);
+            image_column(k, g.ndata, g.split != 0, c, false, dim, part);
             float x = 0.0f;
             if (valid && dim >= 0) x = __fsub_rn(__ldg(col + (size_t)dim * LB), hdr[dim]);
             __nv_bfloat16 o = bf16_part(x, part);
@@ -395,13 +410,29 @@ tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int
 // ---------------------------------------------------------------------------------------------
 // query-side preparation (per search call)
 // ---------------------------------------------------------------------------------------------
+// E(q) >= |S~ - S| + |d_V0 - D'| for every reference (see the file header), a = |q'|, rmax = max |r'|:
+//   operand rounding: plain BF16 2^-7 (1 + 2^-9) a rmax; split precision drops only ql.rl and the
+//   second-order remainders: 2 * 3.1 * 2^-18 a rmax.  The MMA's FP32 accumulation is charged 2^-21 per
+//   term (truncating adders); FP32 |r'|^2 and its 3-term split (KP + 5) 2^-24 rmax^2; centring and V0's
+//   own rounding (KP + 8) 2^-24 (a + rmax)^2; 5 % on top.
+__host__ __device__ inline float tensor_error_bound(bool split, int KP, float a, float rmax)
+{
+    const float u24 = 5.9604645e-8f;
+    const float c_round = split ? 6.2f * 3.8146973e-6f : 0.0078125f * 1.002f;
+    const float E = (c_round + (float)KP * 2.04f * 4.7683716e-7f) * a * rmax + (KP + 5) * u24 * rmax * rmax +
+                    (KP + 8) * u24 * (a + rmax) * (a + rmax);
+    return E * 1.05f;
+}
+
 // one CTA per 256-query strip: BF16 image of -2 q' (TensorGeom layout, 1 in the norm columns),
 // band[q] = 2 E(q), approx_min[q] = +INF (ordered encoding)
 __global__ void __launch_bounds__(256)
 tensor_query_image_kernel(const float* __restrict__ queries, const int m, const int k, const TensorGeom g,
                           const float* __restrict__ hdr, unsigned char* __restrict__ image,
-                          float* __restrict__ band, unsigned* __restrict__ approx_min)
+                          float* __restrict__ band, unsigned* __restrict__ approx_min,
+                          const unsigned* __restrict__ mode_word, const unsigned my_mode)
 {
+    if (tensor_mode_mismatch(mode_word, my_mode)) return;
     const int row = threadIdx.x;
     const long long q = (long long)blockIdx.x * T_BM + row;
     const bool valid = q < m;
@@ -419,7 +450,7 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         for (int e = 0; e < 8; ++e) {
             const int col = ch * 8 + e;
             int dim, part;
-            image_column(k, g.ndata, col, true, dim, part);
+            image_column(k, g.ndata, g.split != 0, col, true, dim, part);
             float x = 0.0f;
             if (valid && dim >= 0) x = __fsub_rn(__ldg(queries + q * k + dim), hdr[dim]);
             __nv_bfloat16 o = bf16_part(-2.0f * x, part);
@@ -436,14 +467,7 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         //   centring + V0 rounding           (K+8) 2^-24 (|q'| + |r'|)^2
         const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[THDR_MAX]);
         const float a = sqrtf(qn), rmax = sqrtf(r2);
-        const float u24 = 5.9604645e-8f;
-        // operand rounding: plain BF16 2^-7 (1 + 2^-9) |q'||r'|; split precision drops only
-        // ql.rl and the second-order remainders: 2 * 3.1 * 2^-18 |q'||r'|.  The MMA's FP32
-        // accumulation is charged 2^-21 per term (truncating adders).
-        const float c_round = tensor_split(k) ? 6.2f * 3.8146973e-6f : 0.0078125f * 1.002f;
-        float E = (c_round + (float)KP * 2.04f * 4.7683716e-7f) * a * rmax + (KP + 5) * u24 * r2 +
-                  (KP + 8) * u24 * (a + rmax) * (a + rmax);
-        E *= 1.05f;
+        const float E = tensor_error_bound(g.split != 0, KP, a, rmax);
         const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[THDR_FLAGS] & 1u) != 0;  // NaN / INF / huge references
         const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f);  // false for NaN too
         band[q] = usable ? 2.0f * E : inf_f();
@@ -503,8 +527,10 @@ template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS>
 __global__ void __maxnreg__(T_MAX_REGS)
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
-                     const float* __restrict__ band, unsigned* __restrict__ approx_min, const CandBuf cb)
+                     const float* __restrict__ band, unsigned* __restrict__ approx_min, const CandBuf cb,
+                     const unsigned* __restrict__ mode_word, const unsigned my_mode)
 {
+    if (tensor_mode_mismatch(mode_word, my_mode)) return;  // the other precision variant of this launch pair runs
     // KB 64-column swizzled blocks (one 128-byte swizzle row each), then KS interleaved 16-column steps
     constexpr uint32_t A_MAIN = KB * T_BM * 128, B_MAIN = KB * T_BN * 128;
     constexpr uint32_t A_BYTES = (uint32_t)image_bytes(T_BM, KB, KS);  // 72 KiB at KB = 2, KS = 1
@@ -899,7 +925,7 @@ cudaError_t tensor_section_init(int k, int n, const float* d_blocks, float* d_se
                                 cudaStream_t st)
 {
     if (tensor_section_floats(k, n) == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(d_section, 0, TENSOR_HDR_FLOATS * sizeof(float), st);
+    cudaError_t e = cudaMemsetAsync(d_section, 0, TENSOR_HDR_FLOATS * sizeof(float), st);  // mode word: 0 = split
     if (e != cudaSuccess) return e;
     TensorCentre c{};
     if (fixed) {
@@ -919,12 +945,56 @@ cudaError_t tensor_image_build(int k, int cn, const float* d_blocks_part, float*
 {
     const int nb = write_blocks > 0 ? write_blocks : (cn + LB - 1) / LB;
     if (nb <= 0 || k < 1 || k > TENSOR_MAX_K) return cudaSuccess;
-    const TensorGeom g = tensor_geom(k);
-    tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks_part, cn, k, g, d_hdr, max_word, flag_word, dst);
+    const TensorGeom g = tensor_geom(k);  // slices of a shared index: always the default (split) layout
+    tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks_part, cn, k, g, d_hdr, max_word, flag_word, dst, nullptr, 0u);
     return cudaGetLastError();
 }
 
-cudaError_t tensor_index_build(int k, int n, const float* d_blocks, float* d_section, cudaStream_t st)
+// ---- precision-mode probe (TENSOR_PLAIN_MIN_K <= k <= TENSOR_SPLIT_MAX_K) ----
+constexpr int TENSOR_PROBE_SAMPLES = 128;
+bool tensor_has_modes(int k) { return k >= TENSOR_PLAIN_MIN_K && k <= TENSOR_SPLIT_MAX_K; }
+
+// sample s = reference number s * stride, copied out of the tiled-SoA blocks as an AoS query
+__global__ void tensor_probe_gather_kernel(const float* __restrict__ blocks, const int n, const int k, const long long stride,
+                                           float* __restrict__ out)
+{
+    const long long j = (long long)blockIdx.x * stride;
+    if (j >= n) return;
+    for (int t = threadIdx.x; t < k; t += blockDim.x)
+        out[(size_t)blockIdx.x * k + t] = blocks[(size_t)(j >> 7) * (k + 1) * LB + (size_t)t * LB + (j & (LB - 1))];
+}
+
+// One warp.  For every sample: d1 = distance to its nearest OTHER reference (second entry of its 2-NN list;
+// 0 for duplicated points), E = the plain-BF16 error bound at that point; (1 + 2E/d1)^(k/2) estimates how
+// many references fall inside the plain band (locally uniform density in k dimensions -- an over-estimate
+// for data of lower intrinsic dimension, which errs towards split precision).  Plain mode is chosen when
+// that estimate is <= 32 for three quarters of the samples.
+__global__ void tensor_mode_kernel(float* __restrict__ hdr, const float* __restrict__ index_header, const float* __restrict__ samples,
+                                   const u64* __restrict__ keys2, const int count, const int k, const int KP_plain)
+{
+    const int lane = (int)threadIdx.x;
+    float c2 = 0.0f;
+    for (int t = 0; t < k; ++t) c2 = __fmaf_rn(hdr[t], hdr[t], c2);
+    // max |r - c| <= max |r| + |c|  (the images, and with them the exact max |r'|^2, do not exist yet)
+    const float rmax = sqrtf(__uint_as_float(reinterpret_cast<const unsigned*>(index_header)[0])) + sqrtf(c2);
+    int ok = 0;
+    for (int s = lane; s < count; s += 32) {
+        float qn = 0.0f;
+        for (int t = 0; t < k; ++t) {
+            const float x = samples[(size_t)s * k + t] - hdr[t];
+            qn = __fmaf_rn(x, x, qn);
+        }
+        const float E = tensor_error_bound(false, KP_plain, sqrtf(qn), rmax);
+        const float d1 = __uint_as_float((unsigned)(keys2[(size_t)s * 2 + 1] >> 32));
+        const float est = (d1 > 0.0f && d1 < inf_f()) ? expf(0.5f * (float)k * log1pf(2.0f * E / d1)) : inf_f();
+        ok += (est <= 32.0f) ? 1 : 0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, off);
+    if (lane == 0) reinterpret_cast<unsigned*>(hdr)[THDR_MODE] = (rmax <= 1e15f && 4 * ok >= 3 * count) ? 1u : 0u;
+}
+
+cudaError_t tensor_index_build(int k, int n, const float* d_header, const float* d_blocks, float* d_section, cudaStream_t st)
 {
     if (tensor_section_floats(k, n) == 0) return cudaSuccess;
     cudaError_t e = tensor_section_init(k, n, d_blocks, d_section, nullptr, st);
@@ -932,7 +1002,38 @@ cudaError_t tensor_index_build(int k, int n, const float* d_blocks, float* d_sec
     ImageDsts dst{};
     dst.p[0] = reinterpret_cast<unsigned char*>(d_section + TENSOR_HDR_FLOATS);
     dst.count = 1;
-    return tensor_image_build(k, n, d_blocks, d_section, THDR_MAX, THDR_FLAGS, dst, st);
+    const int nb = (n + LB - 1) / LB;
+    const unsigned* mode_word = reinterpret_cast<const unsigned*>(d_section) + THDR_MODE;
+    const bool modes = tensor_has_modes(k) && n >= 4 * TENSOR_PROBE_SAMPLES && d_header != nullptr;
+    if (modes) {
+        // probe: the 2 nearest references of TENSOR_PROBE_SAMPLES sample points (the exact FP32 top-K kernel)
+        const int S = TENSOR_PROBE_SAMPLES;
+        const int splits = topk_choose_splits(S, n, 148);
+        const size_t off_keys = ((size_t)S * k * sizeof(float) + 255) & ~(size_t)255;
+        const size_t off_scr = off_keys + (((size_t)S * 2 * sizeof(u64) + 255) & ~(size_t)255);
+        unsigned char* tmp = nullptr;
+        e = cudaMallocAsync((void**)&tmp, off_scr + topk_scratch_bytes(S, 2, splits), st);
+        if (e != cudaSuccess) return e;
+        float* samples = reinterpret_cast<float*>(tmp);
+        u64* keys2 = reinterpret_cast<u64*>(tmp + off_keys);
+        tensor_probe_gather_kernel<<<S, 32, 0, st>>>(d_blocks, n, k, (long long)n / S, samples);
+        e = launch_keys_init(keys2, 2 * S, st);
+        if (e == cudaSuccess) e = topk_search_launch(k, S, n, 2, samples, d_blocks, 0, keys2, reinterpret_cast<u64*>(tmp + off_scr), splits, false, st, nullptr);
+        if (e == cudaSuccess) {
+            const TensorGeom gp = tensor_geom(k, true);
+            tensor_mode_kernel<<<1, 32, 0, st>>>(d_section, d_header, samples, keys2, S, k, gp.KB * 64 + gp.KS * 16);
+            e = cudaGetLastError();
+        }
+        const cudaError_t fe = cudaFreeAsync(tmp, st);
+        if (e != cudaSuccess) return e;
+        if (fe != cudaSuccess) return fe;
+    }
+    // the image in the layout of the chosen mode (both launches; the one that does not match exits at once)
+    tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks, n, k, tensor_geom(k, false), d_section, THDR_MAX, THDR_FLAGS, dst,
+                                                modes ? mode_word : nullptr, 0u);
+    if (modes)
+        tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks, n, k, tensor_geom(k, true), d_section, THDR_MAX, THDR_FLAGS, dst, mode_word, 1u);
+    return cudaGetLastError();
 }
 
 // reference tiles per TMA stage / ring depth per operand geometry (stage = G tiles <= 36 KiB)
@@ -955,18 +1056,45 @@ static size_t tensor_smem_bytes(const TensorGeom& g)
 template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS>
 static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
                                         const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
-                                        const CandBuf& cb)
+                                        const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
 {
     cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb);
+    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb,
+                                                                                          mode_word, my_mode);
     return cudaGetLastError();
 }
 
-__global__ void tensor_status_init_kernel(unsigned* __restrict__ status, const unsigned cap, unsigned* __restrict__ common, const int nbatches)
+// the screen kernel instantiated for operand geometry g: short contractions (k <= 9, or plain mid-k): SS form,
+// 4 buffers of 64 references; longer ones: A in TMEM (NNS_T_TS), 64-reference units in 3 buffers (2 where A
+// needs more than 128 columns)
+static cudaError_t tensor_screen_dispatch(const TensorGeom& g, dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage,
+                                          int m, const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
+                                          const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
+{
+#define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_, NBUF_, TS_) \
+    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode)
+    if (g.KB == 0 && g.KS == 1) return NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false);
+    if (g.KB == 0) return NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false);
+#if NNS_T_TS
+    if (g.KB == 1 && g.KS == 0) return NNS_SCREEN(1, 0, 8, 1, 2, 3, true);
+    if (g.KB == 1) return NNS_SCREEN(1, 1, 8, 1, 2, 3, true);
+    if (g.KS == 0) return NNS_SCREEN(2, 0, 5, 1, 2, 3, true);
+    return NNS_SCREEN(2, 1, 5, 1, 2, 2, true);
+#else
+    if (g.KB == 1 && g.KS == 0) return NNS_SCREEN(1, 0, 8, 1, 1, 2, false);
+    if (g.KB == 1) return NNS_SCREEN(1, 1, 6, 1, 1, 2, false);
+    if (g.KS == 0) return NNS_SCREEN(2, 0, 4, 1, 1, 2, false);
+    return NNS_SCREEN(2, 1, 4, 1, 1, 2, false);
+#endif
+#undef NNS_SCREEN
+}
+
+__global__ void tensor_status_init_kernel(unsigned* __restrict__ status, const unsigned cap, unsigned* __restrict__ common, const int nbatches,
+                                          const unsigned* __restrict__ mode_word, const unsigned kp_split, const unsigned kp_plain)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { status[0] = 0u; status[1] = 0u; status[2] = cap; }
+    if (i == 0) { status[0] = 0u; status[1] = 0u; status[2] = cap; status[3] = (mode_word && *mode_word) ? kp_plain : kp_split; }
     if (i < nbatches) common[i] = 0u;
 }
 
@@ -989,12 +1117,16 @@ static size_t tensor_record_budget()
 // (BASELINE config C5: ~400 32-reference units per query inside the 2E band at n = 16.7 M) stays on
 // the tensor cores instead of overflowing into the FP32 fallback.
 // d_stats: [0] candidates emitted, [1] overflow flag (the caller launches the FP32 fallback kernel with
-// it as its enable flag), [2] candidate capacity of one batch.
+// it as its enable flag), [2] candidate capacity of one batch, [3] contraction length (BF16 columns) of the
+// precision mode the index chose.
 cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const float* d_blocks, const float* d_section,
                           int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
                           int* launches, unsigned* d_stats, bool tiny_candidate_buffer)
 {
-    const TensorGeom g = tensor_geom(k);
+    const TensorGeom g = tensor_geom(k);            // default layout (split where it exists): sizes the scratch
+    const TensorGeom gp = tensor_geom(k, true);     // plain layout, used when the index header says so
+    const bool modes = tensor_has_modes(k);
+    const unsigned* mode_word = modes ? reinterpret_cast<const unsigned*>(d_section) + THDR_MODE : nullptr;
     const int nblocks = (n + LB - 1) / LB;
     const int strips = (m + T_BM - 1) / T_BM;
     const float* hdr = d_section;
@@ -1079,12 +1211,14 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     cb.status = d_stats;
 
     tensor_status_init_kernel<<<(nbatches + 255) / 256, 256, 0, st>>>(d_stats, (unsigned)std::min<size_t>(cand_records, 0xffffffffu),
-                                                                      common_counts, nbatches);
+                                                                      common_counts, nbatches, mode_word,
+                                                                      (unsigned)(g.KB * 64 + g.KS * 16), (unsigned)(gp.KB * 64 + gp.KS * 16));
     e = cudaGetLastError();
     int nl = 1;
     // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
     // CTA is resident per SM even at KP = 64
     const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
+    const size_t smem_plain = std::max(tensor_smem_bytes(gp), (size_t)120 * 1024);
     for (int b = 0; b < nbatches && e == cudaSuccess; ++b) {
         const int s0 = b * batch_strips;
         const int bs = std::min(batch_strips, strips - s0);
@@ -1093,28 +1227,17 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         const float* bq = d_queries + (size_t)q0 * k;
         cb.common_count = common_counts + b;
         cb.n_ctas = (unsigned)bs * (unsigned)splits;  // the common region follows the regions actually used
-        tensor_query_image_kernel<<<bs, 256, 0, st>>>(bq, bm, k, g, hdr, scratch, band, amin);
+        // query image + screen in the layout the index was built in; for the k range that has two precision
+        // modes both variants are launched and the one that does not match the header word exits at once
+        dim3 grid((unsigned)bs, (unsigned)splits);
+        tensor_query_image_kernel<<<bs, 256, 0, st>>>(bq, bm, k, g, hdr, scratch, band, amin, mode_word, 0u);
+        if (modes) tensor_query_image_kernel<<<bs, 256, 0, st>>>(bq, bm, k, gp, hdr, scratch, band, amin, mode_word, 1u);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
-        dim3 grid((unsigned)bs, (unsigned)splits);
-#define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_, NBUF_, TS_) \
-    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_>(grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb)
-        // short contractions (k <= 9): SS form, 4 buffers of 64 references; longer ones: A in TMEM (NNS_T_TS),
-        // 64-reference units in 3 buffers (2 where A needs more than 128 columns)
-        if (g.KB == 0 && g.KS == 1) e = NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false);
-        else if (g.KB == 0) e = NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false);
-#if NNS_T_TS
-        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1, 2, 3, true);
-        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 8, 1, 2, 3, true);
-        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 5, 1, 2, 3, true);
-        else e = NNS_SCREEN(2, 1, 5, 1, 2, 2, true);
-#else
-        else if (g.KB == 1 && g.KS == 0) e = NNS_SCREEN(1, 0, 8, 1, 1, 2, false);
-        else if (g.KB == 1) e = NNS_SCREEN(1, 1, 6, 1, 1, 2, false);
-        else if (g.KS == 0) e = NNS_SCREEN(2, 0, 4, 1, 1, 2, false);
-        else e = NNS_SCREEN(2, 1, 4, 1, 1, 2, false);
-#endif
-#undef NNS_SCREEN
+        e = tensor_screen_dispatch(g, grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 0u);
+        if (e == cudaSuccess && modes)
+            e = tensor_screen_dispatch(gp, grid, smem_plain, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 1u);
+        nl += modes ? 2 : 0;
         if (e != cudaSuccess) break;
         const int rgrid = num_sms * 8;
         if (exact)

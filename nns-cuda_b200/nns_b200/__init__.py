@@ -227,9 +227,9 @@ def tensor_kp(k: int) -> int:
 
 
 def tensor_stats() -> dict:
-    out = (c_uint * 3)()
+    out = (c_uint * 4)()
     _check(lib.nns_b200_tensor_stats(out))
-    return {"candidates": int(out[0]), "overflow": int(out[1]), "capacity": int(out[2])}
+    return {"candidates": int(out[0]), "overflow": int(out[1]), "capacity": int(out[2]), "kp": int(out[3])}
 
 
 def index_floats(k: int, n: int) -> int:

@@ -655,3 +655,27 @@ def test_topk_matches_the_v0_form_oracle(nns, oracle, torch_mod, kind, k, m, n, 
     if n > 0 and kind != "uniform":
         v, _ = oracle.v0_omp(k, m, n, s, r)
         assert np.array_equal(hi[:, 0], v)
+
+
+def test_precision_mode_probe_picks_plain_or_split_per_index(nns, oracle, torch_mod):
+    """For 10 <= k <= 42 the index build probes the data (2-NN distances of sample points vs the plain-BF16
+    error band) and builds plain BF16 operand images (a third of the tensor work) when the band is
+    selective, split-precision ones otherwise.  Uniform 16-D data -> plain (32 columns); the same points
+    squeezed onto a 2-D sheet inside the 16-D cube -> split (64 columns).  Both answers must be V0's."""
+    torch = torch_mod
+    k, m, n = 16, 2048, 400_000
+    s, r = make_case("uniform", k, m, n, 71)
+    for name, want_kp in (("uniform", 32), ("sheet", 64)):
+        if name == "sheet":  # coordinates 2..15 are tiny multiples of the first two: intrinsic dimension 2
+            rr, ss = r.copy(), s.copy()
+            for t in range(2, k):
+                rr[:, t] = np.float32(0.5) + np.float32(1e-3) * (rr[:, t % 2] * np.float32(t))
+                ss[:, t] = np.float32(0.5) + np.float32(1e-3) * (ss[:, t % 2] * np.float32(t))
+        else:
+            rr, ss = r, s
+        v, _ = oracle.v0_omp(k, m, n, ss, rr)
+        index = nns.DeviceIndex(dev(torch, rr))
+        g = index.search(dev(torch, ss), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+        st = nns.tensor_stats()
+        assert st["overflow"] == 0 and st["kp"] == want_kp, (name, st)
+        assert np.array_equal(g, v), (name, int((g != v).sum()))

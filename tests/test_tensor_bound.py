@@ -32,8 +32,10 @@ def trunc32(x64):
     return np.where(over, np.nextafter(t, F32(0)), t).astype(F32)
 
 
-def geometry(k):
-    ndata = 3 * k if k <= 42 else k
+def geometry(k, plain=False):
+    """(contraction length, data columns): split-precision columns up to k = 42 unless the index chose the
+    plain BF16 layout (tensor_geom(k, plain) in csrc/tensor_search.cu; plain exists for 10 <= k <= 42)"""
+    ndata = 3 * k if (k <= 42 and not plain) else k
     for kp in (16, 32, 64):
         if ndata + 3 <= kp:
             return kp, ndata
@@ -42,10 +44,10 @@ def geometry(k):
     return (128, ndata) if ndata + 3 <= 128 else (144, 128)
 
 
-def screen_scores(k, s, r):
+def screen_scores(k, s, r, plain=False):
     """(S~ [m][n], E [m], |q'|^2 exact [m]) as the kernels compute them"""
-    split = k <= 42
-    kp, _ = geometry(k)
+    split = k <= 42 and not plain
+    kp, _ = geometry(k, plain)
     c = (r.astype(F32).sum(axis=0, dtype=F32) / F32(len(r))).astype(F32)  # any centre works; the kernel uses the FP32 mean
     qc = (s - c).astype(F32)
     rc = (r - c).astype(F32)
@@ -95,9 +97,10 @@ def v0_distances(s, r):
 CASES = ["uniform", "clustered", "offset1000", "scale1e-3", "mixed", "one_outlier"]
 
 
-@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128])
+@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, -10, -16, -29, -30, -42])
 @pytest.mark.parametrize("case", CASES)
 def test_screen_error_stays_inside_the_band(k, case):
+    plain, k = k < 0, abs(k)  # negative = the plain BF16 layout of a k that also has the split one
     m, n = 48, 1536
     if case == "clustered" and k == 3:
         s, r = make_case("clustered", k, m, n, 11)
@@ -114,7 +117,7 @@ def test_screen_error_stays_inside_the_band(k, case):
     elif case == "one_outlier":
         r[3] = 300.0
     s, r = s.astype(F32), r.astype(F32)
-    acc, E, qn64 = screen_scores(k, s, r)
+    acc, E, qn64 = screen_scores(k, s, r, plain)
     d = v0_distances(s, r).astype(np.float64)
     err = np.abs(acc.astype(np.float64) + qn64[:, None] - d)
     worst = (err / E[:, None].astype(np.float64)).max()
@@ -124,7 +127,8 @@ def test_screen_error_stays_inside_the_band(k, case):
         assert (E.astype(np.float64) < 0.05 * d.max(axis=1)).all()
 
 
-@pytest.mark.parametrize("k,case", [(3, "uniform"), (3, "clustered"), (16, "uniform"), (16, "mixed"), (128, "uniform"), (64, "offset1000")])
+@pytest.mark.parametrize("k,case", [(3, "uniform"), (3, "clustered"), (16, "uniform"), (16, "mixed"), (128, "uniform"), (64, "offset1000"),
+                                    (-16, "uniform"), (-16, "mixed"), (-30, "offset1000")])
 def test_screen_and_rescore_logic_returns_v0(k, case):
     """The screen's control logic on top of the emulated scores, as the kernels run it: per query a
     running minimum over 32-reference units in index order, a unit is recorded when its minimum is
@@ -132,6 +136,7 @@ def test_screen_and_rescore_logic_returns_v0(k, case):
     re-scored exactly (V0's FP32 distances), and the smallest packed (distance, index) key wins.
     Whatever the unit order and the rounding of the scores, the answer must be V0's: first minimum
     of the FP32 distances.  (Grid-snapped clustered data: many exact ties.)"""
+    plain, k = k < 0, abs(k)
     m, n = 40, 2048
     if case == "clustered":
         s, r = make_case("clustered", k, m, n, 3)
@@ -142,7 +147,7 @@ def test_screen_and_rescore_logic_returns_v0(k, case):
         if case == "mixed":
             r = r.copy()
             r[::7] *= F32(50.0)
-    acc, E, _ = screen_scores(k, s, r)
+    acc, E, _ = screen_scores(k, s, r, plain)
     d = v0_distances(s, r)
     v0 = d.argmin(axis=1)  # numpy argmin = first minimum = V0's strict '>' update (core.cu:44)
     band = (F32(2.0) * E).astype(F32)
@@ -158,5 +163,5 @@ def test_screen_and_rescore_logic_returns_v0(k, case):
         total_candidates += len(live)
         best = min((d[q, j], j) for u in live for j in range(32 * u, 32 * u + 32))
         assert best[1] == v0[q], (q, best, v0[q], d[q, v0[q]])
-    if case != "mixed":  # references 50x farther out inflate max |r'| and with it the band: still exact, no longer selective
+    if case != "mixed" and not (plain and case == "offset1000"):  # references 50x farther out inflate max |r'| and with it the band: still exact, no longer selective
         assert total_candidates < m * (n // 32) // 2  # the screen screens
