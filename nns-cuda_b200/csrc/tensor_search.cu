@@ -66,7 +66,7 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
 #endif
 #ifndef NNS_T_TS
-#define NNS_T_TS 1          // 1 = contractions of 64 columns and more keep the A operand in tensor memory
+#define NNS_T_TS 1          // A operand in tensor memory: 0 = never, 1 = contractions of 64 / 80 columns, 2 = also 128 / 144
 #endif
 #ifndef NNS_T_EXPERIMENT
 #define NNS_T_EXPERIMENT 0  // timing experiments only (wrong results): 1 = epilogue reduces 2 of 32 columns,
@@ -964,6 +964,26 @@ __global__ void tensor_probe_gather_kernel(const float* __restrict__ blocks, con
         out[(size_t)blockIdx.x * k + t] = blocks[(size_t)(j >> 7) * (k + 1) * LB + (size_t)t * LB + (j & (LB - 1))];
 }
 
+// max |r - c|^2 over the strided block sample the centre came from (the images, and with them the exact
+// maximum, do not exist yet when the mode is chosen; an estimate is enough for a heuristic): hdr[THDR_MAX + 4]
+__global__ void __launch_bounds__(128)
+tensor_rmax_sample_kernel(const float* __restrict__ blocks, const int n, const int k, const int stride, float* __restrict__ hdr)
+{
+    const long long b = (long long)blockIdx.x * stride;
+    const long long j = b * LB + threadIdx.x;
+    float rn = 0.0f;
+    if (j < n) {
+        const float* col = blocks + (size_t)b * (k + 1) * LB + threadIdx.x;
+        for (int t = 0; t < k; ++t) {
+            const float x = __ldg(col + (size_t)t * LB) - hdr[t];
+            rn = __fmaf_rn(x, x, rn);
+        }
+    }
+    unsigned bits = (rn < inf_f()) ? __float_as_uint(rn) : 0u;
+    bits = __reduce_max_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + THDR_MAX + 4, bits);
+}
+
 // One warp.  For every sample: d1 = distance to its nearest OTHER reference (second entry of its 2-NN list;
 // 0 for duplicated points), E = the plain-BF16 error bound at that point; (1 + 2E/d1)^(k/2) estimates how
 // many references fall inside the plain band (locally uniform density in k dimensions -- an over-estimate
@@ -973,10 +993,8 @@ __global__ void tensor_mode_kernel(float* __restrict__ hdr, const float* __restr
                                    const u64* __restrict__ keys2, const int count, const int k, const int KP_plain)
 {
     const int lane = (int)threadIdx.x;
-    float c2 = 0.0f;
-    for (int t = 0; t < k; ++t) c2 = __fmaf_rn(hdr[t], hdr[t], c2);
-    // max |r - c| <= max |r| + |c|  (the images, and with them the exact max |r'|^2, do not exist yet)
-    const float rmax = sqrtf(__uint_as_float(reinterpret_cast<const unsigned*>(index_header)[0])) + sqrtf(c2);
+    (void)index_header;
+    const float rmax = sqrtf(__uint_as_float(reinterpret_cast<const unsigned*>(hdr)[THDR_MAX + 4]));  // sampled max |r'|
     int ok = 0;
     for (int s = lane; s < count; s += 32) {
         float qn = 0.0f;
@@ -1016,6 +1034,8 @@ cudaError_t tensor_index_build(int k, int n, const float* d_header, const float*
         if (e != cudaSuccess) return e;
         float* samples = reinterpret_cast<float*>(tmp);
         u64* keys2 = reinterpret_cast<u64*>(tmp + off_keys);
+        const int stride = (nb + TENSOR_CENTRE_BLOCKS - 1) / TENSOR_CENTRE_BLOCKS;
+        tensor_rmax_sample_kernel<<<(nb + stride - 1) / stride, 128, 0, st>>>(d_blocks, n, k, stride, d_section);
         tensor_probe_gather_kernel<<<S, 32, 0, st>>>(d_blocks, n, k, (long long)n / S, samples);
         e = launch_keys_init(keys2, 2 * S, st);
         if (e == cudaSuccess) e = topk_search_launch(k, S, n, 2, samples, d_blocks, 0, keys2, reinterpret_cast<u64*>(tmp + off_scr), splits, false, st, nullptr);
@@ -1042,13 +1062,14 @@ static int tensor_group(const TensorGeom& g) { return g.KB == 0 ? (g.KS == 1 ? 4
 static int tensor_stages(const TensorGeom& g)
 {
     if (g.KB == 0) return 6;
-    if (NNS_T_TS) return g.KB == 2 ? 5 : 8;
+    if (NNS_T_TS == 2) return g.KB == 2 ? 5 : 8;
+    if (NNS_T_TS == 1) return g.KB == 2 ? 4 : 8;
     return g.KB == 2 ? 4 : (g.KS == 0 ? 8 : 6);
 }
 
 static size_t tensor_smem_bytes(const TensorGeom& g)
 {
-    const bool ts = NNS_T_TS && g.KB > 0;  // A lives in TMEM: no shared-memory A tile
+    const bool ts = (NNS_T_TS == 2 && g.KB > 0) || (NNS_T_TS == 1 && g.KB == 1);  // A lives in TMEM: no shared-memory A tile
     return (ts ? 0 : image_bytes(T_BM, g.KB, g.KS)) + (size_t)tensor_stages(g) * tensor_group(g) * image_bytes(T_BN, g.KB, g.KS) +
            (2 * T_MAX_STAGES + 8) * 8 + 16;
 }
@@ -1076,7 +1097,15 @@ static cudaError_t tensor_screen_dispatch(const TensorGeom& g, dim3 grid, size_t
     tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode)
     if (g.KB == 0 && g.KS == 1) return NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false);
     if (g.KB == 0) return NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false);
-#if NNS_T_TS
+#if NNS_T_TS == 1
+    // measured on B200 (profiles/r2_tune_ts.txt): A in TMEM + three 64-reference buffers is 3 % faster at 64
+    // columns (C3 split: 434 vs 446 ms) and 3 % slower at 144 (C4: 229 vs 223 ms), where the tensor pipe is busy
+    // 98 % of the time either way and twice as many MMA instructions only cost issue slots
+    if (g.KB == 1 && g.KS == 0) return NNS_SCREEN(1, 0, 8, 1, 2, 3, true);
+    if (g.KB == 1) return NNS_SCREEN(1, 1, 8, 1, 2, 3, true);
+    if (g.KS == 0) return NNS_SCREEN(2, 0, 4, 1, 1, 2, false);
+    return NNS_SCREEN(2, 1, 4, 1, 1, 2, false);
+#elif NNS_T_TS == 2
     if (g.KB == 1 && g.KS == 0) return NNS_SCREEN(1, 0, 8, 1, 2, 3, true);
     if (g.KB == 1) return NNS_SCREEN(1, 1, 8, 1, 2, 3, true);
     if (g.KS == 0) return NNS_SCREEN(2, 0, 5, 1, 2, 3, true);
