@@ -123,7 +123,10 @@ int make_plan(int k, int m, int n, unsigned flags, int num_sms, occ_fn occ, void
     const bool tensor_ok = k <= TENSOR_MAX_K;
     if ((flags & NNS_B200_FLAG_FORCE_TENSOR) && !tensor_ok)
         return fail(NNS_B200_ERR_UNSUPPORTED, "tensor path needs k <= %d", TENSOR_MAX_K);
-    const bool tensor_auto = k > LOWK_MAX_K ? m >= 256 : (lowk_prefers_tensor(k, m, n) && !(flags & NNS_B200_FLAG_EXACT_FORM));
+    // EXACT_FORM asks for V0's formulation on every pair: never the screen (k > 32: the wide kernel);
+    // k > 32: the screen needs whole 256-query strips and enough pairs to amortise its fixed cost
+    const bool tensor_auto = !(flags & NNS_B200_FLAG_EXACT_FORM) &&
+                             (k > LOWK_MAX_K ? (m >= 256 && (double)m * (double)n >= 1e7) : lowk_prefers_tensor(k, m, n));
     if (tensor_ok && !(flags & (NNS_B200_FLAG_FORCE_WIDE | NNS_B200_FLAG_FORCE_LOWK)) &&
         ((flags & NNS_B200_FLAG_FORCE_TENSOR) || tensor_auto)) {
         // tcgen05 path: one CTA per 256-query strip x reference range (splits chosen at launch)

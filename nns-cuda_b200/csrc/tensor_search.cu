@@ -65,6 +65,9 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #ifndef NNS_T_SPIN
 #define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
 #endif
+#ifndef NNS_T_PIPE
+#define NNS_T_PIPE 0        // 64-reference units: software-pipelined epilogue (a TMEM load in flight under every reduction,
+#endif                      // two units per loop trip, ONE candidate test per two units); 0 = one 64-column load per unit
 #ifndef NNS_T_TS
 #define NNS_T_TS 1          // A operand in tensor memory: 0 = never, 1 = contractions of 64 / 80 columns, 2 = also 128 / 144
 #endif
@@ -167,6 +170,20 @@ __device__ __forceinline__ bool elect_one_sync()
     return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same, tied to the 32 destination registers of a load that may still be in flight: the compiler sees the
+// wait as the definition of v[], so no use of v[] can be scheduled above it (the pipelined epilogue keeps a
+// load in flight across a whole reduction of the other register set)
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :
+        : "memory");
+}
 
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 128 B (64 bf16),
 // 8-row swizzle atoms 1024 B apart (stride byte offset), version 1 (Blackwell).
@@ -769,6 +786,95 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 }
             }
         };
+        // ---- pipelined epilogue for 64-reference units (SUB = 2) ----
+        // ncu source view of the one-load-per-unit loop on C2 (profiles/r2_ncu_c2_screen.txt): a quarter of an
+        // epilogue warp's time went to branch resolution (three taken branches per unit: the loop back edge and
+        // the two jumps over the candidate path), 16 % to waiting for its TMEM load, 14 % to waiting for the next
+        // accumulator.  Here a unit is read as two 32-column halves into two register sets that rotate, so that
+        // a load is in flight under every 32-value reduction; the loop body covers two units, and the four chunk
+        // minima are tested against the threshold ONCE (a threshold that is one unit stale only admits more
+        // candidates), so a trip has two taken branches instead of six.
+        if constexpr (NNS_T_PIPE && CPU == 2 && NNS_T_EXPERIMENT == 0) {
+            uint32_t va[32], vb[32];
+            const int nunits = nt * SUB;
+            auto min32 = [&](const uint32_t (&cur)[32]) -> float {
+                float c0 = min3(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]));
+                float c1 = min3(__uint_as_float(cur[8]), __uint_as_float(cur[9]), __uint_as_float(cur[10]));
+                float c2 = min3(__uint_as_float(cur[16]), __uint_as_float(cur[17]), __uint_as_float(cur[18]));
+                float c3 = min3(__uint_as_float(cur[24]), __uint_as_float(cur[25]), __uint_as_float(cur[26]));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    c0 = min3(c0, __uint_as_float(cur[3 + 2 * j]), __uint_as_float(cur[4 + 2 * j]));
+                    c1 = min3(c1, __uint_as_float(cur[11 + 2 * j]), __uint_as_float(cur[12 + 2 * j]));
+                    c2 = min3(c2, __uint_as_float(cur[19 + 2 * j]), __uint_as_float(cur[20 + 2 * j]));
+                    c3 = min3(c3, __uint_as_float(cur[27 + 2 * j]), __uint_as_float(cur[28 + 2 * j]));
+                }
+                c0 = min3(c0, __uint_as_float(cur[7]), __uint_as_float(cur[15]));
+                c2 = min3(c2, __uint_as_float(cur[23]), __uint_as_float(cur[31]));
+                return min3(min3(c0, c1, c2), c3, c3);
+            };
+            auto emit = [&](const float cm, const int unit32) {  // rare path
+                if (cm <= thresh) {
+                    TensorCand cnd;
+                    cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
+                    cand_emit(cb, s_cand_count, cta, cnd);
+                    if (cm < run_min) {
+                        run_min = cm;
+                        thresh = run_min + my_band;
+                        atomicMin(approx_min + q, f2ord(run_min));
+                    }
+                }
+            };
+            auto acquire = [&](const int u) {  // unit u's accumulator is complete
+                mbar_wait_hot(acc_full + 8 * (u % NBUF), (uint32_t)((u / NBUF) & 1));
+                tc_fence_after();
+            };
+            auto release = [&](const int u) {  // every TMEM read of this warp for unit u has completed
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * (u % NBUF));
+            };
+            auto col0 = [&](const int u) { return lane_base + (uint32_t)((u % NBUF) * 2 * SN); };
+            // one unit: on entry va = first half (complete), vb = second half (load in flight);
+            // on exit the same for unit un (when it exists)
+            auto step = [&](const int u, const int un, float& m0, float& m1) {
+                m0 = min32(va);
+                tmem_ld_wait_for(vb);
+                release(u);
+                if (un < nunits) {
+                    acquire(un);
+                    tmem_ld32(col0(un), va);
+                }
+                m1 = min32(vb);
+                if (un < nunits) {
+                    tmem_ld_wait_for(va);
+                    tmem_ld32(col0(un) + 32, vb);
+                }
+            };
+            int u = (T_TEAMS == 2 ? team : 0);
+            if (u < nunits) {
+                acquire(u);
+                tmem_ld32(col0(u), va);
+                tmem_ld_wait_for(va);
+                tmem_ld32(col0(u) + 32, vb);
+            }
+#pragma unroll 1
+            for (; u < nunits; u += 2 * T_TEAMS) {
+                const int u1 = u + T_TEAMS, u2 = u + 2 * T_TEAMS;
+                float m0, m1, m2 = inf_f(), m3 = inf_f();
+                step(u, u1, m0, m1);
+                if (u1 < nunits) step(u1, u2, m2, m3);
+                if (min3(fminf(m0, m1), m2, m3) <= thresh) {
+                    const int unit0 = t0 * (T_BN / 32) + u * CPU;
+                    emit(m0, unit0);
+                    emit(m1, unit0 + 1);
+                    if (u1 < nunits) {
+                        emit(m2, unit0 + T_TEAMS * CPU);
+                        emit(m3, unit0 + T_TEAMS * CPU + 1);
+                    }
+                }
+            }
+        } else
         // team i reduces the units u = i, i + 2, ...: buffer u % NBUF (its own parity), 32-reference
         // candidate units t0 * 4 + u * CPU + c
         for (int u = (T_TEAMS == 2 ? team : 0); u < nt * SUB; u += T_TEAMS) {
