@@ -54,6 +54,8 @@ WORKLOADS = {
     # not a BASELINE config: the reference's m = 1 shapes (main.cu:39-42) scaled up -- the low-arithmetic-intensity
     # case the north-star wants reported as achieved HBM GB/s (reference-parallel kernel, 4(k+1)n bytes per call)
     "m1": (16, 1, 16777216, "uniform", "query"),
+    # not a BASELINE config: a contraction longer than the 128 columns of C4 (tcgen05 K-loop kernel, tensor_longk.cu)
+    "k256": (256, 262144, 1048576, "uniform", "query"),
 }
 FP32_LANES_PER_SM = 128
 AGREEMENT_SAMPLE = 256
@@ -250,7 +252,8 @@ def sharding_text(name, world, shard, strong):
 def workload_config(name, n_gpus, sharding, l2):
     k, m, n, kind, _ = WORKLOADS[name]
     return {"workload": f"{name.upper()}: k={k}, m={m} queries, n={n} {kind} fp32 reference points "
-                        + (f"(BASELINE.json configs[{list(WORKLOADS).index(name)}])" if name != "m1" else "(the reference's m = 1 shape, main.cu:39-42, at 16.7 M references)"),
+                        + (f"(BASELINE.json configs[{list(WORKLOADS).index(name)}])" if name.startswith("c") else
+                           "(the reference's m = 1 shape, main.cu:39-42, at 16.7 M references)" if name == "m1" else "(not a BASELINE config)"),
             "k": k, "m": m, "n": n, "distribution": kind, "sharding": sharding, "l2": l2, "n_gpus": n_gpus}
 
 

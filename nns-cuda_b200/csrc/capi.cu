@@ -525,7 +525,7 @@ int nns_b200_index_build_part(int k, int n_total, int j0, int cn, int part_block
     TensorCentre c{};
     if (d_section) {
         if (!centre) return fail(NNS_B200_ERR_INVALID, "a part of an index with a tensor section needs a fixed centre");
-        for (int t = 0; t < k && t < 128; ++t) c.c[t] = centre[t];
+        for (int t = 0; t < k && t < 512; ++t) c.c[t] = centre[t];
         CU_TRY(tensor_section_init(k, n_total, nullptr, d_section, &c, st));
     }
     BlockDsts dst{};

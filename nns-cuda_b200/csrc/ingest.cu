@@ -169,9 +169,9 @@ int h2d_async(DeviceCtx* c, void* d_dst, const void* h_src, size_t bytes, cudaSt
 void sample_centre_host(int k, int n, const float* r_points, TensorCentre* out)
 {
     memset(out, 0, sizeof(*out));
-    if (n <= 0 || k > 128) return;
+    if (n <= 0 || k > 512) return;
     const int samples = n < 4096 ? n : 4096;
-    double sum[128] = {0.0};
+    double sum[512] = {0.0};
     for (int i = 0; i < samples; ++i) {
         const float* row = r_points + (size_t)((long long)i * n / samples) * k;
         for (int t = 0; t < k; ++t) {
@@ -516,7 +516,7 @@ int nns_b200_search_topk_host(int k, int m, int n, int K, const float* s_points,
 
 int nns_b200_sample_centre(int k, int n, const float* r_points, float* centre_out)
 {
-    if (k <= 0 || k > 128 || n < 0 || !centre_out || (n > 0 && !r_points)) return fail(NNS_B200_ERR_INVALID, "invalid arguments");
+    if (k <= 0 || k > 512 || n < 0 || !centre_out || (n > 0 && !r_points)) return fail(NNS_B200_ERR_INVALID, "invalid arguments");
     TensorCentre c;
     sample_centre_host(k, n, r_points, &c);
     for (int t = 0; t < k; ++t) centre_out[t] = c.c[t];

@@ -8,16 +8,16 @@ namespace nns {
 
 // ---- headers ----
 // index header (INDEX_HEADER_FLOATS words): [0] max |r|^2 (bits); [HDR_PART_MAX + g] the same of GPU g's slice
-// tensor section header (TENSOR_HDR_FLOATS words): [0..127] centre, [THDR_MAX] max |r'|^2 (bits),
+// tensor section header (TENSOR_HDR_FLOATS words): [0..511] centre, [THDR_MAX] max |r'|^2 (bits),
 // [THDR_FLAGS] bit 0: unusable; [THDR_PART_MAX + g], [THDR_PART_FLAGS + g] per-GPU partials (multi-GPU ingest)
 constexpr int MAX_PEERS = 8;
 constexpr int HDR_PART_MAX = 8;
-constexpr int THDR_MAX = 128, THDR_FLAGS = 129, THDR_MODE = 131, THDR_PART_MAX = 136, THDR_PART_FLAGS = 152;
+constexpr int THDR_MAX = 512, THDR_FLAGS = 513, THDR_MODE = 515, THDR_PART_MAX = 520, THDR_PART_FLAGS = 536;
 // [THDR_MODE] 0 = split-precision operand images, 1 = plain BF16 (only for TENSOR_PLAIN_MIN_K <= k <= TENSOR_SPLIT_MAX_K)
 struct BlockDsts { float* p[MAX_PEERS]; int count; };            // first block of the part in every destination index
 struct ImageDsts { unsigned char* p[MAX_PEERS]; int count; };    // first tile image of the part in every destination
 struct HeaderPeers { float* header[MAX_PEERS]; float* section[MAX_PEERS]; int count; int self; };
-struct TensorCentre { float c[128]; };                           // a caller-fixed centre, passed by value
+struct TensorCentre { float c[512]; };                           // a caller-fixed centre, passed by value
 
 // index_build.cu
 cudaError_t launch_index_build(int k, int n, const float* d_refs_aos, float* d_header, float* d_blocks,
@@ -48,13 +48,13 @@ struct WideArgs {
 cudaError_t wide_launch(bool exact, const WideArgs& a);
 
 // tensor_search.cu -- tcgen05 path for k <= TENSOR_MAX_K (split-precision BF16 up to TENSOR_SPLIT_MAX_K)
-constexpr int TENSOR_MAX_K = 128;
+constexpr int TENSOR_MAX_K = 509;    // 8 blocks of 64 columns incl. the 3 norm columns (tensor_longk.cu above 128)
 #ifndef NNS_T_SPLIT_MAX
 #define NNS_T_SPLIT_MAX 42
 #endif
 constexpr int TENSOR_SPLIT_MAX_K = NNS_T_SPLIT_MAX;  // 3k <= 128 contraction columns
 constexpr int TENSOR_PLAIN_MIN_K = 10;  // below, the plain band is never selective enough (k = 3: 2E = 6e-3 vs d^2 ~ 4e-5)
-constexpr int TENSOR_HDR_FLOATS = 256;  // [0..127] centre, [128] max |r'|^2 bits, [129] flags
+constexpr int TENSOR_HDR_FLOATS = 1024;  // [0..127] centre, [128] max |r'|^2 bits, [129] flags
 int tensor_kp(int k);
 size_t tensor_section_floats(int k, int n);
 size_t tensor_image_bytes_per_block(int k);

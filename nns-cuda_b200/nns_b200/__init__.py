@@ -223,7 +223,9 @@ def tensor_kp(k: int) -> int:
         return 80
     if ndata + 3 <= 128:
         return 128
-    return 144
+    if ndata <= 128:
+        return 144
+    return 64 * ((ndata + 3 + 63) // 64)
 
 
 def tensor_stats() -> dict:

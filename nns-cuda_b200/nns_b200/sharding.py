@@ -94,7 +94,7 @@ def gather_built_index(k: int, n: int, r_host, rank: int, world: int, device, st
     index = torch.empty(nns_b200.index_floats(k, n_pad), dtype=torch.float32, device=device)
     with torch.cuda.device(device), torch.cuda.stream(st):
         d_part = r_t[j0:j0 + cn].to(device, non_blocking=True) if cn > 0 else torch.empty((0, k), dtype=torch.float32, device=device)
-        centre = nns_b200.sample_centre(k, n, r_np) if k <= 128 else None
+        centre = nns_b200.sample_centre(k, n, r_np) if k <= 509 else None
         _check(lib.nns_b200_index_build_part(k, n_pad, j0, cn, per_blocks, d_part.data_ptr(), index.data_ptr(),
                                              centre.ctypes.data if centre is not None else None, rank, ctypes.c_void_p(st.cuda_stream)))
         if world > 1:

@@ -53,31 +53,33 @@ def tensor_geometry(k):
         return 1, 1
     if ndata + 3 <= 128:
         return 2, 0
-    return 2, 1
+    if ndata <= 128:
+        return 2, 1
+    return (ndata + 3 + 63) // 64, 0  # 128 < k <= 509: whole 64-column blocks, K-loop kernel (tensor_longk.cu)
 
 
 def test_index_geometry(nns):
-    # 32-float header + (k coordinate rows + 1 norm row) x 128 lanes per block of 128 points, then (k <= 128)
-    # the tensor section: 256-float header + per block a BF16 operand image of 128 rows x (KB * 128 + KS * 32) B
+    # 32-float header + (k coordinate rows + 1 norm row) x 128 lanes per block of 128 points, then (k <= 509)
+    # the tensor section: 1024-float header + per block a BF16 operand image of 128 rows x (KB * 128 + KS * 32) B
     def floats(k, n):
         if n <= 0:
             return 0
         nb = (n + 127) // 128
         total = 32 + nb * (k + 1) * 128
-        if k <= 128:
+        if k <= 509:
             kb, ks = tensor_geometry(k)
-            total += 256 + nb * 128 * (kb * 128 + ks * 32) // 4
+            total += 1024 + nb * 128 * (kb * 128 + ks * 32) // 4
         return total
 
     assert nns.index_floats(3, 0) == 0
-    assert [tensor_geometry(k) for k in (1, 3, 4, 5, 9, 10, 16, 20, 21, 41, 42, 43, 61, 62, 64, 65, 125, 126, 128)] == [
+    assert [tensor_geometry(k) for k in (1, 3, 4, 5, 9, 10, 16, 20, 21, 41, 42, 43, 61, 62, 64, 65, 125, 126, 128, 129, 189, 190, 317, 318, 509)] == [
         (0, 1), (0, 1), (0, 1), (0, 2), (0, 2), (1, 0), (1, 0), (1, 0), (1, 1), (2, 0), (2, 1), (1, 0), (1, 0), (1, 1),
-        (1, 1), (2, 0), (2, 0), (2, 1), (2, 1)]
+        (1, 1), (2, 0), (2, 0), (2, 1), (2, 1), (3, 0), (3, 0), (4, 0), (5, 0), (6, 0), (8, 0)]
     for k, n in [(3, 1), (3, 129), (16, 16777216), (128, 128), (40, 129), (50, 129), (129, 128), (3, 128), (22, 128),
-                 (4, 1000), (5, 1000), (10, 77), (21, 4096), (64, 300), (200, 5)]:
+                 (4, 1000), (5, 1000), (10, 77), (21, 4096), (64, 300), (200, 5), (509, 300), (510, 300), (1000, 5)]:
         assert nns.index_floats(k, n) == floats(k, n), (k, n)
-    assert nns.index_floats(3, 1) == 32 + 4 * 128 + 256 + 128 * 32 // 4  # k = 3: one K = 16 step per reference
-    assert nns.index_floats(129, 128) == 32 + 130 * 128                  # k > 128: no tensor section
+    assert nns.index_floats(3, 1) == 32 + 4 * 128 + 1024 + 128 * 32 // 4  # k = 3: one K = 16 step per reference
+    assert nns.index_floats(510, 128) == 32 + 511 * 128                   # k > 509: no tensor section
     assert nns.lib.nns_b200_workspace_bytes(3, 10, 129) >= (32 + 2 * 4 * 128) * 4 + 80
 
 
@@ -122,7 +124,9 @@ def test_plan_paths(nns):
     assert p["smem"] <= 227 * 1024
     assert nns.plan(128, 1024, 65536)["path"] == 2  # 32 < k <= 128, m >= 256 -> tcgen05 path
     assert nns.plan(128, 100, 65536)["path"] == 1  # few queries -> reference-parallel FP32 kernel
-    assert nns.plan(200, 1024, 65536)["path"] == 1  # k > 128 -> reference-parallel FP32 kernel
+    assert nns.plan(200, 1024, 65536)["path"] == 2  # 128 < k <= 509 -> tcgen05 K-loop kernel
+    assert nns.plan(600, 1024, 65536)["path"] == 1  # k > 509 -> reference-parallel FP32 kernel
+    assert nns.plan(128, 1024, 65536, nns.FLAG_EXACT_FORM)["path"] == 1  # V0's formulation on every pair: never the screen
     assert nns.plan(3, 1, 65536)["path"] == 1  # the reference's m = 1 shapes are reference-parallel
     assert nns.plan(3, 1, 65536, nns.FLAG_FORCE_LOWK)["path"] == 0
     assert nns.plan(3, 4096, 65536, nns.FLAG_FORCE_WIDE)["path"] == 1

@@ -679,3 +679,49 @@ def test_precision_mode_probe_picks_plain_or_split_per_index(nns, oracle, torch_
         st = nns.tensor_stats()
         assert st["overflow"] == 0 and st["kp"] == want_kp, (name, st)
         assert np.array_equal(g, v), (name, int((g != v).sum()))
+
+
+# ---- tcgen05 K-loop kernel, 128 < k <= 509 (tensor_longk.cu) ---------------------------------------
+@pytest.mark.parametrize("k,m,n", [(129, 300, 5000), (200, 513, 12345), (256, 1024, 40000), (317, 700, 9000), (318, 700, 9000),
+                                   (400, 256, 8192), (509, 1000, 6000), (192, 257, 129)])
+def test_long_contractions_on_the_tensor_cores(nns, oracle, torch_mod, k, m, n):
+    """k > 128: the K-loop screen (A resident in shared memory, one 64-column block of B per stage; 256 query rows
+    per CTA up to k = 317, 128 above) + exact FP32 re-score must return V0's indices (V0 rounding -> identical)."""
+    torch = torch_mod
+    s, r = make_case("uniform", k, m, n, 81)
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    assert nns.plan(k, m, n, nns.FLAG_FORCE_TENSOR)["path"] == 2
+    index = nns.DeviceIndex(dev(torch, r))
+    g = index.search(dev(torch, s), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+    st = nns.tensor_stats()
+    assert st["overflow"] == 0 and st["kp"] == 64 * ((k + 3 + 63) // 64), st
+    assert np.array_equal(g, v), int((g != v).sum())
+    # two reference shards (index_base) + the default FMA rounding under the tie rule
+    h = (n // 2 + 127) // 128 * 128
+    if 0 < h < n:
+        keys = None
+        for r0, r1 in ((h, n), (0, h)):
+            part = nns.DeviceIndex(dev(torch, r[r0:r1]), index_base=r0)
+            keys = part.new_keys(m) if keys is None else keys
+            part.search_keys(dev(torch, s), keys, nns.FLAG_FORCE_TENSOR)
+        g2 = nns.unpack_keys(keys, m).cpu().numpy()
+        rep = oracle.check_tie_rule(k, m, n, s, r, g2, v, REL_TOL)
+        assert rep["violations"] == 0 and rep["exact_match_with_v0"] >= m - 2, rep
+
+
+def test_long_contraction_adversarial(nns, oracle, torch_mod):
+    """k = 200 with duplicates, an offset, NaN / INF coordinates and all-identical points (overflow -> FP32 fallback)."""
+    torch = torch_mod
+    k, m, n = 200, 300, 4000
+    s, r = make_case("uniform", k, m, n, 83)
+    cases = {}
+    rr = r.copy(); rr[64::64] = rr[27:27 + len(rr[64::64])]; ss = s.copy(); ss[::2] = rr[(np.arange(0, m, 2) * 37) % n]
+    cases["duplicates"] = (ss, rr)
+    cases["offset"] = ((s + np.float32(100.0)).astype(np.float32), (r + np.float32(100.0)).astype(np.float32))
+    rn = r.copy(); rn[5, 3] = np.nan; rn[77, 0] = np.inf; rn[1000] = np.nan
+    cases["nan_inf"] = (s, rn)
+    cases["all_identical"] = (s, np.tile(r[:1], (n, 1)))
+    for name, (a, b) in cases.items():
+        v, _ = oracle.v0_omp(k, m, n, a, b)
+        g = nns.DeviceIndex(dev(torch, b)).search(dev(torch, a), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+        assert np.array_equal(g, v), (name, int((g != v).sum()), nns.tensor_stats())

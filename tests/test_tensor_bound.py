@@ -41,7 +41,9 @@ def geometry(k, plain=False):
             return kp, ndata
     if ndata <= 64:
         return 80, 64
-    return (128, ndata) if ndata + 3 <= 128 else (144, 128)
+    if ndata <= 128:
+        return (128, ndata) if ndata + 3 <= 128 else (144, 128)
+    return 64 * ((ndata + 3 + 63) // 64), ndata  # K-loop kernel: whole 64-column blocks
 
 
 def screen_scores(k, s, r, plain=False):
@@ -97,7 +99,7 @@ def v0_distances(s, r):
 CASES = ["uniform", "clustered", "offset1000", "scale1e-3", "mixed", "one_outlier"]
 
 
-@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, -10, -16, -29, -30, -42])
+@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, 129, 200, 320, 509, -10, -16, -29, -30, -42])
 @pytest.mark.parametrize("case", CASES)
 def test_screen_error_stays_inside_the_band(k, case):
     plain, k = k < 0, abs(k)  # negative = the plain BF16 layout of a k that also has the split one
