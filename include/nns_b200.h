@@ -100,6 +100,20 @@ int nns_b200_index_search(nns_b200_index_t *index, int m, const float *s_points,
 int nns_b200_index_size(const nns_b200_index_t *index, int *k, int *n);
 int nns_b200_index_destroy(nns_b200_index_t *index);
 
+/* ---- exact search through a bucketed KD-tree (k <= 32) -----------------------------------------
+ * What the reference's v10 / v11 were meant to be (core.cu:1059-1163: CPU KD-tree; core.cu:1289-1451: GPU
+ * KD-tree whose kernel body is commented out and which therefore returns zeros): the tree is built on the
+ * host by median splits in an implicit heap layout like the reference's (core.cu:1072-1114), its leaves
+ * are 128-point blocks in the engine's tiled-SoA layout, and the search runs on the GPU, one warp per
+ * query, with exactly the brute-force kernels' FP32 distance arithmetic -- the answers are V0's
+ * (lowest index on exact ties, index 0 when no distance is < +INF), not approximations.  For low k and many
+ * references it visits a few leaves per query instead of all n points.  distances may be NULL. */
+typedef struct nns_b200_tree nns_b200_tree_t;
+int nns_b200_tree_create(int k, int n, const float *r_points, int device, nns_b200_tree_t **out);
+int nns_b200_tree_search(nns_b200_tree_t *tree, int m, const float *s_points, int *results,
+                         float *distances);
+int nns_b200_tree_destroy(nns_b200_tree_t *tree);
+
 /* ---- lifetime ----------------------------------------------------------------------------
  * Replaces the load-time WarmUP static initialiser (core.cu:1900-1933): nothing touches the
  * GPU at load; nns_b200_init(device) creates the per-device state eagerly (device < 0 = the

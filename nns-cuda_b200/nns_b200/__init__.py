@@ -82,6 +82,9 @@ lib.nns_b200_index_create.argtypes = [c_int, c_int, c_void_p, c_int, POINTER(c_v
 lib.nns_b200_index_search.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
 lib.nns_b200_index_size.argtypes = [c_void_p, POINTER(c_int), POINTER(c_int)]
 lib.nns_b200_index_destroy.argtypes = [c_void_p]
+lib.nns_b200_tree_create.argtypes = [c_int, c_int, c_void_p, c_int, POINTER(c_void_p)]
+lib.nns_b200_tree_search.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+lib.nns_b200_tree_destroy.argtypes = [c_void_p]
 lib.nns_b200_sample_centre.argtypes = [c_int, c_int, c_void_p, c_void_p]
 lib.nns_b200_index_build_part.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
 lib.nns_b200_index_part_ranges.argtypes = [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]
@@ -187,6 +190,36 @@ def search_topk_host(k: int, m: int, n: int, K: int, s_points, r_points, return_
     _check(lib.nns_b200_search_topk_host(k, m, n, K, s.ctypes.data, r.ctypes.data, idx.ctypes.data,
                                          dist.ctypes.data if return_dist else None))
     return (idx, dist) if return_dist else idx
+
+
+class HostTree:
+    """nns_b200_tree_*: exact nearest-neighbour search through a bucketed KD-tree (k <= 32) built from a host
+    array; searches take host query arrays and return V0's indices."""
+
+    def __init__(self, k: int, n: int, r_points, device: int = -1):
+        self.k, self.n = int(k), int(n)
+        r = _host_f32(r_points, n, k)
+        h = c_void_p()
+        _check(lib.nns_b200_tree_create(k, n, r.ctypes.data, device, ctypes.byref(h)))
+        self._h = h
+
+    def search(self, m: int, s_points, return_dist: bool = False):
+        s = _host_f32(s_points, m, self.k)
+        out = np.empty(m, dtype=np.int32)
+        dist = np.empty(m, dtype=np.float32) if return_dist else None
+        _check(lib.nns_b200_tree_search(self._h, m, s.ctypes.data, out.ctypes.data, dist.ctypes.data if return_dist else None))
+        return (out, dist) if return_dist else out
+
+    def close(self):
+        if self._h:
+            _check(lib.nns_b200_tree_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def sample_centre(k: int, n: int, r_points) -> np.ndarray:
