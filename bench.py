@@ -585,6 +585,35 @@ def ref_gpu_record():
     return rec
 
 
+def tree_record():
+    """Side record (not the metric): the exact KD-tree path (csrc/kdtree.cu, SURVEY 8f row n4 -- the reference's
+    V11 is an empty stub) on C2's shape: build time (upload + Morton sort + leaves + boxes on the GPU), search time
+    through nns_b200_tree_search with host
+    arrays, and agreement with the brute-force answer of the same library and with V0 on a sample."""
+    import nns_b200
+
+    k, m, n = 3, 65536, 4194304
+    _, _, _, s, r = make_inputs("c2", 0)
+    t0 = time.perf_counter()
+    tree = nns_b200.HostTree(k, n, r)
+    build_s = time.perf_counter() - t0
+    tree.search(1024, s[:1024])
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        g = tree.search(m, s)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    brute = nns_b200.search_host(k, m, n, s, r)
+    sample = agreement_sample(m)
+    _, _, v_idx = cpu_reference_rate(k, n, np.ascontiguousarray(s[sample]), r, 1)
+    tree.close()
+    return {"workload": "C2's shape through the exact KD-tree (k=3, m=65536, n=4194304)", "build_ms": build_s * 1e3,
+            "build": "nns_b200_tree_create: host array in, upload + GPU Morton-order build (first call: includes one-time allocations)",
+            "search_ms": min(ts), "search_ms_median": statistics.median(ts),
+            "timing": "wall clock around nns_b200_tree_search (query upload + search + download)",
+            "identical_to_brute_force": float((g == brute).mean()), "identical_to_v0_sample": float((g[sample] == v_idx).mean())}
+
+
 def run_multi_api(args):
     """--api multi: ONE process, host arrays, nns_b200_search_multi on N GPUs -- the reference's V8/V9 shape
     (core.cu:965-1057).  Wall clock around the whole call (everything is inside: uploads over N PCIe links,
@@ -708,6 +737,11 @@ def main():
             rg = ref_gpu_record()
             if rg:
                 line["ref_gpu"] = rg
+            if recs:  # the default (driver) run only
+                try:
+                    line["tree"] = tree_record()
+                except Exception as e:  # a side record never fails the bench
+                    line["tree"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

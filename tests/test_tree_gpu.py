@@ -2,6 +2,7 @@
 meant to be (core.cu:1289-1451 returns zeros: its kernel body is commented out).  It is an EXACT search: on
 every input the indices must be V0's -- lowest index on exact ties, NaN never wins, index 0 when nothing is
 below +INF -- whatever the tree prunes."""
+import os
 import time
 
 import numpy as np
@@ -10,6 +11,19 @@ import pytest
 from conftest import make_case
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["gpu_build", "host_build"], autouse=True)
+def build_mode(request):
+    """Both builds fill the same structure: Morton order on the GPU (default), median splits on the host
+    (NNS_B200_TREE_HOST_BUILD=1, the reference's way); the search must return V0's answer over either."""
+    old = os.environ.get("NNS_B200_TREE_HOST_BUILD")
+    os.environ["NNS_B200_TREE_HOST_BUILD"] = "1" if request.param == "host_build" else "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("NNS_B200_TREE_HOST_BUILD", None)
+    else:
+        os.environ["NNS_B200_TREE_HOST_BUILD"] = old
 
 
 @pytest.mark.parametrize("kind,k,m,n", [("uniform", 3, 1024, 65536), ("clustered", 3, 4000, 300_000), ("grid", 3, 500, 20_000),
@@ -56,7 +70,7 @@ def test_tree_special_values_and_duplicates(nns, oracle):
     tree.close()
 
 
-def test_tree_visits_a_sliver_of_the_references_at_low_k(nns, oracle):
+def test_tree_visits_a_sliver_of_the_references_at_low_k(nns, oracle, build_mode):
     """k = 3, n = 2^22: the tree answers 65,536 queries much faster than the brute-force path of the same
     library needs for the same answer (it scans a few of the 32,768 leaves per query)."""
     k, m, n = 3, 65536, 1 << 22
@@ -72,7 +86,7 @@ def test_tree_visits_a_sliver_of_the_references_at_low_k(nns, oracle):
     t0 = time.perf_counter()
     b = nns.search_host(k, m, n, s, r)
     t_brute = time.perf_counter() - t0
-    print(f"tree build {t_build:.2f} s (host), tree search {t_tree * 1e3:.2f} ms, brute force {t_brute * 1e3:.2f} ms (incl. upload of the references)")
+    print(f"[{build_mode}] tree build {t_build * 1e3:.1f} ms, tree search {t_tree * 1e3:.2f} ms, brute force {t_brute * 1e3:.2f} ms (incl. upload of the references)")
     sample = np.random.default_rng(9).permutation(m)[:512]
     v, _ = oracle.v0_omp(k, 512, n, s[sample], r)
     rep = oracle.check_tie_rule(k, 512, n, s[sample], r, g[sample], v, 1e-5)
