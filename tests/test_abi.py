@@ -97,6 +97,46 @@ def test_argument_validation_needs_no_gpu(nns):
         nns.plan(0, 1, 1)
 
 
+def test_extension_entry_points_validate_before_touching_the_gpu(nns):
+    import ctypes
+
+    s = np.zeros((4, 3), np.float32)
+    out = np.zeros((4, 4), np.int32)
+    # K nearest neighbours: K must be 1..32, k <= 1024
+    assert nns.lib.nns_b200_search_topk_host(3, 4, 4, 0, s.ctypes.data, s.ctypes.data, out.ctypes.data, None) == nns.ERR_UNSUPPORTED
+    assert nns.lib.nns_b200_search_topk_host(3, 4, 4, 33, s.ctypes.data, s.ctypes.data, out.ctypes.data, None) == nns.ERR_UNSUPPORTED
+    assert nns.lib.nns_b200_search_topk_host(0, 4, 4, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data, None) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_search_topk_host(3, 0, 4, 4, s.ctypes.data, s.ctypes.data, out.ctypes.data, None) == nns.OK
+    # tree: k <= 32
+    h = ctypes.c_void_p()
+    assert nns.lib.nns_b200_tree_create(0, 4, s.ctypes.data, -1, ctypes.byref(h)) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_tree_create(33, 4, s.ctypes.data, -1, ctypes.byref(h)) == nns.ERR_UNSUPPORTED
+    assert nns.lib.nns_b200_tree_create(3, 4, None, -1, ctypes.byref(h)) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_tree_search(None, 4, s.ctypes.data, out.ctypes.data, None) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_tree_destroy(None) == nns.OK
+    # handles and parts
+    assert nns.lib.nns_b200_index_create(0, 4, s.ctypes.data, -1, ctypes.byref(h)) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_index_search(None, 4, s.ctypes.data, out.ctypes.data, None) == nns.ERR_INVALID
+    assert nns.lib.nns_b200_index_destroy(None) == nns.OK
+    c = np.zeros(3, np.float32)
+    assert nns.lib.nns_b200_sample_centre(3, 4, s.ctypes.data, c.ctypes.data) == nns.OK
+    assert nns.lib.nns_b200_sample_centre(600, 4, s.ctypes.data, c.ctypes.data) == nns.ERR_INVALID
+    rg = (ctypes.c_size_t * 6)()
+    assert nns.lib.nns_b200_index_part_ranges(3, 1024, 128, 4, 1, rg) == nns.OK
+    assert rg[0] == (32 + 1 * 4 * 128) * 4 and rg[1] == 4 * 4 * 128 * 4  # blocks of part 1 start after block 0; 4 blocks
+    assert rg[4] == (8 + 1) * 4                                           # its slot in the index header
+    assert nns.lib.nns_b200_index_part_ranges(3, 1024, 100, 4, 1, rg) == nns.ERR_INVALID  # slices are whole blocks
+
+
+def test_sample_centre_is_the_mean_of_strided_rows(nns):
+    r = np.arange(10000 * 3, dtype=np.float32).reshape(10000, 3)
+    c = nns.sample_centre(3, 10000, r)
+    rows = r[(np.arange(4096, dtype=np.int64) * 10000) // 4096]
+    np.testing.assert_allclose(c, rows.astype(np.float64).mean(0), rtol=1e-6)
+    r[5, 1] = np.nan  # non-finite coordinates do not steer the centre
+    assert np.isfinite(nns.sample_centre(3, 10000, r)).all()
+
+
 def test_no_cpu_fallback_fails_loudly_without_gpu(nns):
     import torch
 
