@@ -58,10 +58,16 @@ void count_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_
 // B200, profiles/r1_tensor_*: C2 (k = 3, 2.7e11 pairs) 18.6 ms vs 39.9 ms, C3 (k = 16) 0.49 s vs 2.6 s,
 // C1 (6.7e7 pairs) 0.38 ms vs 0.064 ms; the reference's largest shape (k = 16, m = 1024, n = 2^20,
 // 1.1e9 pairs) 8.1 ms vs 6.7 ms end to end.  Both paths return identical indices.
+// The crossover is a measured property of this build on B200, not of the algorithm: NNS_B200_TENSOR_MIN_PAIRS
+// (a floating-point pair count) overrides it for other clocks / drivers without a rebuild.
 static bool lowk_prefers_tensor(int k, int m, int n)
 {
+    static const double forced = []() {
+        const char* e = getenv("NNS_B200_TENSOR_MIN_PAIRS");
+        return e ? atof(e) : -1.0;
+    }();
     const double pairs = (double)m * (double)n;
-    return m >= 1024 && pairs >= (k <= 8 ? 4e9 : 2e9);
+    return m >= 1024 && pairs >= (forced >= 0.0 ? forced : (k <= 8 ? 4e9 : 2e9));
 }
 
 // register estimate used when no device is available to ask (tests / nns_b200_plan)

@@ -103,6 +103,19 @@ struct DeviceGuard {
     }
 };
 
+// Wait until everything enqueued on `st` has completed.  cudaStreamSynchronize on a stream that is ALREADY idle
+// was measured to stall for 50-700 ms every few calls on B200 / driver 580 (the stream-ordered pool holds ~2 GB
+// of freed scratch at that point; a download into pageable memory has just returned, so the stream is known to
+// be idle: tools/e2e_probe.py with NNS_B200_TRACE=1).  Asking first costs a microsecond and avoids the call.
+static inline cudaError_t stream_drain(cudaStream_t st)
+{
+    const cudaError_t q = cudaStreamQuery(st);
+    if (q == cudaSuccess) return cudaSuccess;
+    if (q != cudaErrorNotReady) return q;
+    cudaGetLastError();
+    return cudaStreamSynchronize(st);
+}
+
 // The hot path on device-resident data: plan, launch.  The caller must have made c->device current.
 // d_section = tensor section of these n references (NULL: the tcgen05 path is not available).
 int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, const float* d_header,

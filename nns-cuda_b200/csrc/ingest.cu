@@ -9,6 +9,7 @@
 #include <cstring>
 #include <deque>
 #include <thread>
+#include <time.h>
 
 #include "host_state.h"
 
@@ -193,6 +194,16 @@ void sample_centre_host(int k, int n, const float* r_points, TensorCentre* out)
 long long ingest_chunk_points(int k, int n, bool tensor)
 {
     const long long row = (long long)k * 4;
+    // NNS_B200_INGEST_CHUNK_MB (tuning): 0 = the whole set in one chunk, > 0 = that many MiB of AoS data per chunk
+    static const long long forced = []() {
+        const char* e = getenv("NNS_B200_INGEST_CHUNK_MB");
+        return e ? atoll(e) : -1ll;
+    }();
+    if (forced == 0) return ((long long)n + LB - 1) / LB * LB > LB ? ((long long)n + LB - 1) / LB * LB : LB;
+    if (forced > 0) {
+        const long long c = ((forced << 20) / row) / LB * LB;
+        return c < LB ? LB : c;
+    }
     long long chunk = ((32ll << 20) / row) / LB * LB;
     if (tensor && k > LOWK_MAX_K) return ((long long)n + LB - 1) / LB * LB > LB ? ((long long)n + LB - 1) / LB * LB : LB;
     if (tensor) {
@@ -214,9 +225,23 @@ int search_host_on(DeviceCtx* c, int k, int m, int n, const float* s, const floa
     return search_host_locked(c, k, m, n, s, r, index_base, h_keys, h_idx, ext_keys, h_dist);
 }
 
+// NNS_B200_TRACE=1: host-clock phase times of every host-pointer search on stderr (tuning aid)
+static bool ingest_trace()
+{
+    static const bool on = []() { const char* e = getenv("NNS_B200_TRACE"); return e && atoi(e) != 0; }();
+    return on;
+}
+static double now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int search_host_locked(DeviceCtx* c, int k, int m, int n, const float* s, const float* r, int index_base,
                        u64* h_keys, int* h_idx, u64* ext_keys, float* h_dist)
 {
+    const double t_start = now_ms();
     DeviceGuard guard;
     ST_TRY(guard.enter(c->device));
     const unsigned flags = host_flags();
@@ -242,6 +267,7 @@ int search_host_locked(DeviceCtx* c, int k, int m, int n, const float* s, const 
     int* d_idx = (int*)c->idx.p;
     ST_TRY(ctx_events(c, nchunks + 1));
 
+    const double t_reserved = now_ms();
     // queries ride the copy stream ahead of the first reference chunk
     ST_TRY(h2d_async(c, d_q, s, qbytes, c->copy));
     CU_TRY(launch_keys_init(d_keys, m, c->compute));
@@ -249,20 +275,26 @@ int search_host_locked(DeviceCtx* c, int k, int m, int n, const float* s, const 
     for (int ci = 0; ci < nchunks; ++ci) {
         const long long j0 = (long long)ci * chunk;
         const int cn = (int)((n - j0) < chunk ? (n - j0) : chunk);
+        const double tc0 = now_ms();
         ST_TRY(h2d_async(c, d_r + j0 * k, r + j0 * k, (size_t)cn * k * sizeof(float), c->copy));
         CU_TRY(cudaEventRecord(c->events[ci], c->copy));
         CU_TRY(cudaStreamWaitEvent(c->compute, c->events[ci], 0));
         float* d_blocks_c = d_index + INDEX_HEADER_FLOATS + (j0 / LB) * (long long)bf;
         CU_TRY(launch_index_build(k, cn, d_r + j0 * k, d_index, d_blocks_c, ci == 0, c->compute));
         count_launches(1);
+        const double tc1 = now_ms();
         float* d_section_c = nullptr;
         if (tensor) {
             d_section_c = (float*)c->tsec.p + (size_t)ci * chunk_sec_floats;
             CU_TRY(tensor_index_build(k, cn, d_index, d_blocks_c, d_section_c, c->compute));
             count_launches(3);
         }
+        const double tc2 = now_ms();
         ST_TRY(search_keys_on(c, k, m, cn, d_q, d_index, d_blocks_c, d_section_c, index_base + (int)j0, d_keys, flags,
                               c->compute));
+        if (ingest_trace())
+            fprintf(stderr, "nns_b200 trace:   chunk %d: upload+transpose enqueue %.2f ms, tensor build enqueue %.2f ms, search enqueue %.2f ms\n", ci,
+                    tc1 - tc0, tc2 - tc1, now_ms() - tc2);
     }
     if (nchunks == 0) {  // n == 0: still wait for the query upload before the buffers are reused
         CU_TRY(cudaEventRecord(c->events[0], c->copy));
@@ -282,8 +314,23 @@ int search_host_locked(DeviceCtx* c, int k, int m, int n, const float* s, const 
         CU_TRY(cudaMemcpyAsync(h_idx, d_idx, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
         if (h_dist) CU_TRY(cudaMemcpyAsync(h_dist, d_dist, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
     }
-    CU_TRY(cudaStreamSynchronize(c->compute));
-    CU_TRY(cudaStreamSynchronize(c->copy));
+    const double t_enqueued = now_ms();
+    const cudaError_t idle = ingest_trace() ? cudaStreamQuery(c->compute) : cudaSuccess;
+    if (ingest_trace()) fprintf(stderr, "nns_b200 trace:   compute stream after the download returned: %s\n", idle == cudaSuccess ? "idle" : cudaGetErrorName(idle));
+    cudaGetLastError();
+    CU_TRY(stream_drain(c->compute));
+    const double t_sync1 = now_ms();
+    CU_TRY(stream_drain(c->copy));
+    if (ingest_trace()) {
+        unsigned long long res = 0, used = 0, dres = 0;
+        cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrReservedMemCurrent, &res);
+        cudaMemPoolGetAttribute(c->pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        cudaMemPool_t dp;
+        if (cudaDeviceGetDefaultMemPool(&dp, c->device) == cudaSuccess) cudaMemPoolGetAttribute(dp, cudaMemPoolAttrReservedMemCurrent, &dres);
+        fprintf(stderr, "nns_b200 trace: k=%d m=%d n=%d chunks=%d tensor=%d | reserve %.2f ms, enqueue + run %.2f ms, sync compute %.2f ms, sync copy %.2f ms"
+                " | pool reserved %.0f MB used %.0f MB, default pool reserved %.0f MB\n", k, m, n, nchunks, (int)tensor, t_reserved - t_start,
+                t_enqueued - t_reserved, t_sync1 - t_enqueued, now_ms() - t_sync1, res / 1048576.0, used / 1048576.0, dres / 1048576.0);
+    }
     return NNS_B200_OK;
 }
 
@@ -397,7 +444,7 @@ int nns_b200_index_search(nns_b200_index_t* h, int m, const float* s_points, int
     count_launches(2);
     CU_TRY(cudaMemcpyAsync(results, d_idx, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
     if (distances) CU_TRY(cudaMemcpyAsync(distances, d_dist, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
-    CU_TRY(cudaStreamSynchronize(c->compute));
+    CU_TRY(stream_drain(c->compute));
     return NNS_B200_OK;
 }
 
@@ -509,8 +556,8 @@ int nns_b200_search_topk_host(int k, int m, int n, int K, const float* s_points,
     CU_TRY(topk_unpack_launch(d_keys, m, K, d_idx, distances ? d_dist : nullptr, c->compute));
     CU_TRY(cudaMemcpyAsync(indices, d_idx, cells * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
     if (distances) CU_TRY(cudaMemcpyAsync(distances, d_dist, cells * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
-    CU_TRY(cudaStreamSynchronize(c->compute));
-    CU_TRY(cudaStreamSynchronize(c->copy));
+    CU_TRY(stream_drain(c->compute));
+    CU_TRY(stream_drain(c->copy));
     return NNS_B200_OK;
 }
 

@@ -474,7 +474,7 @@ int nns_b200_tree_search(nns_b200_tree_t* h, int m, const float* s_points, int* 
         if (distances) CU_TRY(cudaMemcpyAsync(distances, d_dist, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
     }
     CU_TRY(cudaMemcpyAsync(results, d_idx, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
-    CU_TRY(cudaStreamSynchronize(c->compute));
+    CU_TRY(stream_drain(c->compute));
     return NNS_B200_OK;
 }
 

@@ -181,8 +181,8 @@ static int gather_worker(GatherShared& sh, int g, bool* reached_barriers)
         count_launches(2);
         CU_TRY(cudaMemcpyAsync(sh.results + q0, d_idx, (size_t)qn * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
     }
-    CU_TRY(cudaStreamSynchronize(c->compute));
-    CU_TRY(cudaStreamSynchronize(c->copy));
+    CU_TRY(stream_drain(c->compute));
+    CU_TRY(stream_drain(c->copy));
     return NNS_B200_OK;
 }
 
@@ -313,7 +313,7 @@ extern "C" int nns_b200_search_multi(int k, int m, int n, const float* s_points,
         ST_TRY(buf_reserve(&c0->idx, (size_t)m * sizeof(int)));
         CU_TRY(launch_keys_unpack(shared_keys, m, (int*)c0->idx.p, nullptr, c0->compute));
         CU_TRY(cudaMemcpyAsync(results, c0->idx.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, c0->compute));
-        CU_TRY(cudaStreamSynchronize(c0->compute));
+        CU_TRY(stream_drain(c0->compute));
         count_launches(1);
         return NNS_B200_OK;
     }
