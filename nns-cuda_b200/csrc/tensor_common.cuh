@@ -25,8 +25,12 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
 #endif
 #ifndef NNS_T_PIPE
-#define NNS_T_PIPE 0        // 64-reference units: software-pipelined epilogue (a TMEM load in flight under every reduction,
-#endif                      // two units per loop trip, ONE candidate test per two units); 0 = one 64-column load per unit
+#define NNS_T_PIPE 2        // epilogue of the 64-reference units: 0 = one unit per loop trip, a candidate test per 32-column chunk;
+#endif                      // 2 = NNS_T_TRIP units per trip and ONE test per trip (12 % faster on C2: profiles/r2_tune_trip.txt);
+                            // 1 = additionally two rotating 32-column register sets with a load in flight under every reduction (slower)
+#ifndef NNS_T_TRIP
+#define NNS_T_TRIP 2        // NNS_T_PIPE = 2: units per loop trip / candidate test
+#endif
 #ifndef NNS_T_TS
 #define NNS_T_TS 1          // A operand in tensor memory: 0 = never, 1 = contractions of 64 / 80 columns, 2 = also 128 / 144
 #endif

@@ -511,7 +511,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         // a load is in flight under every 32-value reduction; the loop body covers two units, and the four chunk
         // minima are tested against the threshold ONCE (a threshold that is one unit stale only admits more
         // candidates), so a trip has two taken branches instead of six.
-        if constexpr (NNS_T_PIPE && CPU == 2 && NNS_T_EXPERIMENT == 0) {
+        if constexpr (NNS_T_PIPE == 1 && CPU == 2 && NNS_T_EXPERIMENT == 0) {
             uint32_t va[32], vb[32];
             const int nunits = nt * SUB;
             auto min32 = [&](const uint32_t (&cur)[32]) -> float {
@@ -589,6 +589,72 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                         emit(m2, unit0 + T_TEAMS * CPU);
                         emit(m3, unit0 + T_TEAMS * CPU + 1);
                     }
+                }
+            }
+        } else if constexpr (NNS_T_PIPE == 2 && CPU == 2 && NNS_T_EXPERIMENT == 0) {
+            // ---- variant: one 64-column load per unit as in the default path, but two units per loop trip and ONE
+            // candidate test per two units (fewer taken branches; no change to the TMEM access pattern) ----
+            uint32_t w[64];
+            const int nunits = nt * SUB;
+            auto min32w = [&](const int o) -> float {
+                float c0 = min3(__uint_as_float(w[o + 0]), __uint_as_float(w[o + 1]), __uint_as_float(w[o + 2]));
+                float c1 = min3(__uint_as_float(w[o + 8]), __uint_as_float(w[o + 9]), __uint_as_float(w[o + 10]));
+                float c2 = min3(__uint_as_float(w[o + 16]), __uint_as_float(w[o + 17]), __uint_as_float(w[o + 18]));
+                float c3 = min3(__uint_as_float(w[o + 24]), __uint_as_float(w[o + 25]), __uint_as_float(w[o + 26]));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    c0 = min3(c0, __uint_as_float(w[o + 3 + 2 * j]), __uint_as_float(w[o + 4 + 2 * j]));
+                    c1 = min3(c1, __uint_as_float(w[o + 11 + 2 * j]), __uint_as_float(w[o + 12 + 2 * j]));
+                    c2 = min3(c2, __uint_as_float(w[o + 19 + 2 * j]), __uint_as_float(w[o + 20 + 2 * j]));
+                    c3 = min3(c3, __uint_as_float(w[o + 27 + 2 * j]), __uint_as_float(w[o + 28 + 2 * j]));
+                }
+                c0 = min3(c0, __uint_as_float(w[o + 7]), __uint_as_float(w[o + 15]));
+                c2 = min3(c2, __uint_as_float(w[o + 23]), __uint_as_float(w[o + 31]));
+                return min3(min3(c0, c1, c2), c3, c3);
+            };
+            auto emit2 = [&](const float cm, const int unit32) {
+                if (cm <= thresh) {
+                    TensorCand cnd;
+                    cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
+                    cand_emit(cb, s_cand_count, cta, cnd);
+                    if (cm < run_min) {
+                        run_min = cm;
+                        thresh = run_min + my_band;
+                        atomicMin(approx_min + q, f2ord(run_min));
+                    }
+                }
+            };
+            auto unit = [&](const int u, float& m0, float& m1) {
+                const int buf = u % NBUF;
+                mbar_wait_hot(acc_full + 8 * buf, (uint32_t)((u / NBUF) & 1));
+                tc_fence_after();
+                tmem_ld64(lane_base + (uint32_t)(buf * 2 * SN), w);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                m0 = min32w(0);
+                m1 = min32w(32);
+            };
+            constexpr int TRIP = NNS_T_TRIP;  // units per loop trip and per candidate test
+#pragma unroll 1
+            for (int u = (T_TEAMS == 2 ? team : 0); u < nunits; u += TRIP * T_TEAMS) {
+                float mm[2 * TRIP];
+                float all = inf_f();
+#pragma unroll
+                for (int j = 0; j < TRIP; ++j) {
+                    mm[2 * j] = mm[2 * j + 1] = inf_f();
+                    if (j == 0 || u + j * T_TEAMS < nunits) unit(u + j * T_TEAMS, mm[2 * j], mm[2 * j + 1]);
+                    all = min3(all, mm[2 * j], mm[2 * j + 1]);
+                }
+                if (all <= thresh) {
+                    const int unit0 = t0 * (T_BN / 32) + u * CPU;
+#pragma unroll
+                    for (int j = 0; j < TRIP; ++j)
+                        if (j == 0 || u + j * T_TEAMS < nunits) {
+                            emit2(mm[2 * j], unit0 + j * T_TEAMS * CPU);
+                            emit2(mm[2 * j + 1], unit0 + j * T_TEAMS * CPU + 1);
+                        }
                 }
             }
         } else
