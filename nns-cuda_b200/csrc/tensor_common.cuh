@@ -28,6 +28,9 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #define NNS_T_PIPE 2        // epilogue of the 64-reference units: 0 = one unit per loop trip, a candidate test per 32-column chunk;
 #endif                      // 2 = NNS_T_TRIP units per trip and ONE test per trip (12 % faster on C2: profiles/r2_tune_trip.txt);
                             // 1 = additionally two rotating 32-column register sets with a load in flight under every reduction (slower)
+#ifndef NNS_T_ISS
+#define NNS_T_ISS 2         // MMA-issuing threads of the short-contraction screens (k <= 9, plain mid-k): 1 or 2
+#endif
 #ifndef NNS_T_TRIP
 #define NNS_T_TRIP 2        // NNS_T_PIPE = 2: units per loop trip / candidate test
 #endif

@@ -257,7 +257,12 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
 // what ruled out N = 64 units (A re-read twice as often) for the longer contractions; with A in TMEM the
 // units can be 64 references wide and NBUF = 3 accumulator buffers fit beside A (2 * 3 * 64 + A columns
 // <= 512), so an epilogue team has two unit periods to drain a buffer instead of one.
-template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS>
+// ISS = MMA-issuing threads (warps 1 .. ISS): a thread's mbarrier wait returns ~250 clk after its last
+// tcgen05.commit, so ONE issuer paces 64-reference units at ~265 clk each while their epilogue needs ~150
+// (tools/tensor_trace2.py: the epilogue warps start waiting before the unit is even issued).  With ISS = 2
+// (only for SUB = 2) issuer i issues sub-unit i of every tile into the buffers of team i; both wait for a B
+// stage and both commit its release.
+template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS, int ISS>
 __global__ void __maxnreg__(T_MAX_REGS)
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
@@ -276,6 +281,8 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     static_assert(!TS || A_COL0 + 2 * STEPS * 8 <= 512, "accumulators + A operand exceed the 512 TMEM columns");
     static_assert(TS || 2 * NBUF * SN <= 512, "accumulators exceed the 512 TMEM columns");
     constexpr uint32_t A_SMEM = TS ? 0u : A_BYTES;
+    constexpr int SERVICE = 1 + ISS;           // warp 0 = TMA producer, warps 1 .. ISS = MMA issuers
+    static_assert(ISS == 1 || (ISS == 2 && SUB == 2 && NBUF == 4), "two issuers: sub-unit i of every tile, buffers i and i + 2");
     constexpr int CPU = SN / 32;               // 32-column chunks per unit
     // instruction descriptor: D = F32, A = B = BF16, both K-major, N = SN, M = 128
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -306,7 +313,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < T_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        for (int s = 0; s < T_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, ISS); }
         for (int i = 0; i < NBUF; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_TEAM_WARPS); }
         mbar_init(a_full, TS ? T_TEAM_WARPS : 1);
         mbar_fence_init();
@@ -336,8 +343,8 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 if (++s == T_STAGES) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
+    } else if (warp < SERVICE) {
+        // ---------------- MMA issuer(s) ----------------
         // ONE thread issues every MMA of the CTA, and for short contractions its own instruction
         // stream paces the tile pipeline (ncu source view of the first two-team build: ~550 clk per
         // tile of dependent uniform-datapath arithmetic, ~10 clk per instruction, and an
@@ -375,9 +382,10 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             uint32_t ph = 0;
             uint32_t boff16 = 0;  // (byte offset of the current B tile inside the ring) >> 4: added to the descriptors' start-address field
             // one accumulator unit: references [sub * SN, sub * SN + SN) of the current tile into buffer `buf`
-            auto issue_unit = [&](const int u, const int buf, const int sub) {
+            // tile_first / tile_last: this is the issuing thread's first / last unit of the tile
+            auto issue_unit = [&](const int u, const int buf, const int sub, const bool tile_first, const bool tile_last) {
                 mbar_wait_mma(acc_empty + 8 * buf, (uint32_t)(((u / NBUF) & 1) ^ 1));  // its team drained this buffer
-                if (j == 0 && sub == 0) mbar_wait_mma(b_full + 8 * s, ph);               // TMA landed this stage
+                if (j == 0 && tile_first) mbar_wait_mma(b_full + 8 * s, ph);             // TMA landed this stage
                 tc_fence_after();
                 // rows sub * SN .. of the B tile: SN rows of 128 B in a swizzled block, of 16 B in an interleaved chunk
                 const uint32_t sw16 = boff16 + (uint32_t)(sub * SN * 128 >> 4), il16 = boff16 + (uint32_t)(sub * SN * 16 >> 4);
@@ -405,8 +413,8 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 }
                 tc_commit(acc_full + 8 * buf);   // accumulator complete
                 T_TRACE(3, u);
-                if (sub == SUB - 1) {            // last unit of the tile
-                    if (j == G - 1 || u == nt * SUB - 1) {
+                if (tile_last) {                 // this thread is done with the tile
+                    if (j == G - 1 || u / SUB == nt - 1) {
                         tc_commit(b_empty + 8 * s);  // stage free once the MMAs of its tiles have read it
                         j = 0;
                         if (++s == T_STAGES) { s = 0; ph ^= 1u; }
@@ -417,11 +425,23 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     }
                 }
             };
-            // unrolled over the TMEM buffers: buffer and barrier addresses are immediates
-            for (int u = 0; u < nt * SUB; u += NBUF) {
+            if constexpr (ISS == 1) {
+                // unrolled over the TMEM buffers: buffer and barrier addresses are immediates
+                for (int u = 0; u < nt * SUB; u += NBUF) {
 #pragma unroll
-                for (int i = 0; i < NBUF; ++i)
-                    if (u + i < nt * SUB) issue_unit(u + i, i, (NBUF % SUB == 0) ? i % SUB : (u + i) % SUB);
+                    for (int i = 0; i < NBUF; ++i)
+                        if (u + i < nt * SUB) {
+                            const int sub = (NBUF % SUB == 0) ? i % SUB : (u + i) % SUB;
+                            issue_unit(u + i, i, sub, sub == 0, sub == SUB - 1);
+                        }
+                }
+            } else {
+                // issuer `id` = sub-unit `id` of every tile: units 2 t + id, buffers id and id + 2 alternately
+                const int id = warp - 1;
+                for (int t = 0; t < nt; t += 2) {
+                    issue_unit(2 * t + id, id, id, true, true);
+                    if (t + 1 < nt) issue_unit(2 * (t + 1) + id, id + 2, id, true, true);
+                }
             }
         }
     } else {
@@ -430,7 +450,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         // team has TWO tile periods for the serial path of one tile (wait, four TMEM-load round
         // trips, 76 FMNMX3, release -- ~700 clk measured with tools/tensor_trace.py, of which only
         // 150 clk are issue slots); with 4 epilogue warps per scheduler the ALU pipe stays busy.
-        const int e = warp - T_SERVICE_WARPS;
+        const int e = warp - SERVICE;
         const int team = e >> 3;                // TMEM buffer / tile parity (0 when T_TEAMS == 1)
         const int lq = warp & 3;                // TMEM lane quarter this warp may access
         const int half = (e >> 2) & 1;          // accumulator half (rows 0-127 / 128-255)
@@ -626,13 +646,16 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             };
             auto unit = [&](const int u, float& m0, float& m1) {
                 const int buf = u % NBUF;
+                if (lane == 0) T_TRACE(24 + (e & 7), u);   // [24..31] started waiting (trace rows are per warp of the unit's team)
                 mbar_wait_hot(acc_full + 8 * buf, (uint32_t)((u / NBUF) & 1));
+                if (lane == 0) T_TRACE(4 + (e & 7), u);    // [4..11] accumulator ready
                 tc_fence_after();
                 tmem_ld64(lane_base + (uint32_t)(buf * 2 * SN), w);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                if (lane == 0) T_TRACE(12 + (e & 7), u);   // [12..19] released
                 m0 = min32w(0);
                 m1 = min32w(32);
             };
@@ -963,15 +986,15 @@ static size_t tensor_smem_bytes(const TensorGeom& g)
            (2 * T_MAX_STAGES + 8) * 8 + 16;
 }
 
-template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS>
+template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS, int ISS = 1>
 static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
                                         const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
                                         const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
 {
-    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS><<<grid, T_THREADS, smem, st>>>(qimage, m, rimage, ntiles, tps, band, amin, cb,
-                                                                                          mode_word, my_mode);
+    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS><<<grid, 32 * (1 + ISS + T_TEAMS * T_TEAM_WARPS), smem, st>>>(
+        qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode);
     return cudaGetLastError();
 }
 
@@ -984,8 +1007,10 @@ static cudaError_t tensor_screen_dispatch(const TensorGeom& g, dim3 grid, size_t
 {
 #define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_, NBUF_, TS_) \
     tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode)
-    if (g.KB == 0 && g.KS == 1) return NNS_SCREEN(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false);
-    if (g.KB == 0) return NNS_SCREEN(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false);
+#define NNS_SCREEN_ISS(KB_, KS_, ST_, G_, SUB_, NBUF_, TS_, ISS_) \
+    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_, ISS_>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode)
+    if (g.KB == 0 && g.KS == 1) return NNS_SCREEN_ISS(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false, (NNS_T_SUB == 2 ? NNS_T_ISS : 1));
+    if (g.KB == 0) return NNS_SCREEN_ISS(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false, (NNS_T_SUB == 2 ? NNS_T_ISS : 1));
 #if NNS_T_TS == 1
     // measured on B200 (profiles/r2_tune_ts.txt): A in TMEM + three 64-reference buffers is 3 % faster at 64
     // columns (C3 split: 434 vs 446 ms) and 3 % slower at 144 (C4: 229 vs 223 ms), where the tensor pipe is busy
@@ -1006,6 +1031,7 @@ static cudaError_t tensor_screen_dispatch(const TensorGeom& g, dim3 grid, size_t
     return NNS_SCREEN(2, 1, 4, 1, 1, 2, false);
 #endif
 #undef NNS_SCREEN
+#undef NNS_SCREEN_ISS
 }
 
 __global__ void tensor_status_init_kernel(unsigned* __restrict__ status, const unsigned cap, unsigned* __restrict__ common, const int nbatches,
