@@ -611,6 +611,74 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     }
                 }
             }
+        } else if constexpr (NNS_T_PIPE == 3 && CPU == 2 && NNS_T_EXPERIMENT == 0 && T_TEAMS == 1) {
+            // ---- variant (one team of 8 warps, up to 168 registers per thread): two rotating 64-column register sets,
+            // the load of the next unit in flight under the reduction of the current one ----
+            uint32_t va[64], vb[64];
+            const int nunits = nt * SUB;
+            auto min64 = [&](const uint32_t (&w)[64], float& m0, float& m1) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int o = 32 * hh;
+                    float c0 = min3(__uint_as_float(w[o + 0]), __uint_as_float(w[o + 1]), __uint_as_float(w[o + 2]));
+                    float c1 = min3(__uint_as_float(w[o + 8]), __uint_as_float(w[o + 9]), __uint_as_float(w[o + 10]));
+                    float c2 = min3(__uint_as_float(w[o + 16]), __uint_as_float(w[o + 17]), __uint_as_float(w[o + 18]));
+                    float c3 = min3(__uint_as_float(w[o + 24]), __uint_as_float(w[o + 25]), __uint_as_float(w[o + 26]));
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        c0 = min3(c0, __uint_as_float(w[o + 3 + 2 * j]), __uint_as_float(w[o + 4 + 2 * j]));
+                        c1 = min3(c1, __uint_as_float(w[o + 11 + 2 * j]), __uint_as_float(w[o + 12 + 2 * j]));
+                        c2 = min3(c2, __uint_as_float(w[o + 19 + 2 * j]), __uint_as_float(w[o + 20 + 2 * j]));
+                        c3 = min3(c3, __uint_as_float(w[o + 27 + 2 * j]), __uint_as_float(w[o + 28 + 2 * j]));
+                    }
+                    c0 = min3(c0, __uint_as_float(w[o + 7]), __uint_as_float(w[o + 15]));
+                    c2 = min3(c2, __uint_as_float(w[o + 23]), __uint_as_float(w[o + 31]));
+                    (hh == 0 ? m0 : m1) = min3(min3(c0, c1, c2), c3, c3);
+                }
+            };
+            auto emit3 = [&](const float cm, const int unit32) {
+                if (cm <= thresh) {
+                    TensorCand cnd;
+                    cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
+                    cand_emit(cb, s_cand_count, cta, cnd);
+                    if (cm < run_min) {
+                        run_min = cm;
+                        thresh = run_min + my_band;
+                        atomicMin(approx_min + q, f2ord(run_min));
+                    }
+                }
+            };
+            auto acquire3 = [&](const int u) {
+                mbar_wait_hot(acc_full + 8 * (u % NBUF), (uint32_t)((u / NBUF) & 1));
+                tc_fence_after();
+            };
+            auto release3 = [&](const int u) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * (u % NBUF));
+            };
+            auto col3 = [&](const int u) { return lane_base + (uint32_t)((u % NBUF) * 2 * SN); };
+            if (nunits > 0) { acquire3(0); tmem_ld64(col3(0), va); }
+#pragma unroll 1
+            for (int u = 0; u < nunits; u += 2) {
+                float m0, m1, m2 = inf_f(), m3 = inf_f();
+                tmem_ld_wait_for64(va);
+                release3(u);
+                if (u + 1 < nunits) { acquire3(u + 1); tmem_ld64(col3(u + 1), vb); }
+                min64(va, m0, m1);
+                if (u + 1 < nunits) {
+                    tmem_ld_wait_for64(vb);
+                    release3(u + 1);
+                    if (u + 2 < nunits) { acquire3(u + 2); tmem_ld64(col3(u + 2), va); }
+                    min64(vb, m2, m3);
+                }
+                if (min3(fminf(m0, m1), m2, m3) <= thresh) {
+                    const int unit0 = t0 * (T_BN / 32) + u * CPU;
+                    emit3(m0, unit0);
+                    emit3(m1, unit0 + 1);
+                    if (u + 1 < nunits) { emit3(m2, unit0 + 2); emit3(m3, unit0 + 3); }
+                }
+            }
         } else if constexpr (NNS_T_PIPE == 2 && CPU == 2 && NNS_T_EXPERIMENT == 0) {
             // ---- variant: one 64-column load per unit as in the default path, but two units per loop trip and ONE
             // candidate test per two units (fewer taken branches; no change to the TMEM access pattern) ----
