@@ -402,6 +402,47 @@ int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, co
     return NNS_B200_OK;
 }
 
+// K nearest neighbours: the tcgen05 screen (tensor_topk_search) for large problems, else the FP32 kernel.  The
+// screen's fixed cost (sample pass, image, lists) pays off from ~4e9 pairs; FORCE_TENSOR / FORCE_LOWK / FORCE_WIDE
+// / EXACT_FORM select explicitly (the last three: the FP32 kernel).
+bool topk_wants_tensor(int k, int m, int n, unsigned flags)
+{
+    if (k > TENSOR_MAX_K || n < 64 * LB) return false;
+    if (flags & (NNS_B200_FLAG_FORCE_LOWK | NNS_B200_FLAG_FORCE_WIDE | NNS_B200_FLAG_EXACT_FORM)) return false;
+    if (flags & NNS_B200_FLAG_FORCE_TENSOR) return true;
+    return m >= 1024 && (double)m * (double)n >= 4e9;
+}
+
+int topk_keys_on(DeviceCtx* c, int k, int m, int n, int K, const float* d_queries, const float* d_blocks, const float* d_section,
+                 int index_base, u64* d_keys, unsigned flags, cudaStream_t st)
+{
+    const bool exact = (flags & NNS_B200_FLAG_V0_ROUNDING) != 0;
+    if (d_section && topk_wants_tensor(k, m, n, flags)) {
+        ST_TRY(buf_reserve(&c->stats, 64));
+        unsigned* d_status = nullptr;
+        CU_TRY(cudaMallocFromPoolAsync((void**)&d_status, 64, c->pool, st));
+        int launches = 0;
+        cudaError_t e = tensor_topk_search(k, m, n, K, d_queries, d_blocks, d_section, index_base, d_keys, exact, c->num_sms, st, c->pool,
+                                           &launches, d_status);
+        count_launches(launches);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->stats.p, d_status, 4 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+        const cudaError_t fe = cudaFreeAsync(d_status, st);
+        CU_TRY(e);
+        CU_TRY(fe);
+        return NNS_B200_OK;
+    }
+    const int splits = topk_choose_splits(m, n, c->num_sms);
+    u64* scratch = nullptr;
+    CU_TRY(cudaMallocFromPoolAsync((void**)&scratch, topk_scratch_bytes(m, K, splits), c->pool, st));
+    int launches = 0;
+    const cudaError_t e = topk_search_launch(k, m, n, K, d_queries, d_blocks, index_base, d_keys, scratch, splits, exact, st, &launches);
+    count_launches(launches);
+    const cudaError_t fe = cudaFreeAsync(scratch, st);
+    CU_TRY(e);
+    CU_TRY(fe);
+    return NNS_B200_OK;
+}
+
 // NNS_B200_FLAGS (environment, a C integer literal) applies the flags word to the host-pointer
 // entry points, whose reference signature has no flags argument.
 unsigned host_flags()
@@ -615,18 +656,9 @@ int nns_b200_topk_keys(int k, int m, int n, int K, const float* d_queries, const
     if (m == 0 || n == 0) return NNS_B200_OK;
     DeviceCtx* c;
     ST_TRY(ctx_get(-1, &c));
-    cudaStream_t st = (cudaStream_t)stream;
-    const int splits = topk_choose_splits(m, n, c->num_sms);
-    u64* scratch = nullptr;
-    CU_TRY(cudaMallocFromPoolAsync((void**)&scratch, topk_scratch_bytes(m, K, splits), c->pool, st));
-    int launches = 0;
-    const cudaError_t e = topk_search_launch(k, m, n, K, d_queries, d_index + INDEX_HEADER_FLOATS, index_base, (u64*)d_keys, scratch,
-                                             splits, (flags & NNS_B200_FLAG_V0_ROUNDING) != 0, st, &launches);
-    count_launches(launches);
-    const cudaError_t fe = cudaFreeAsync(scratch, st);
-    CU_TRY(e);
-    CU_TRY(fe);
-    return NNS_B200_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return topk_keys_on(c, k, m, n, K, d_queries, d_index + INDEX_HEADER_FLOATS, section_of(k, n, (float*)d_index), index_base,
+                        (u64*)d_keys, flags, (cudaStream_t)stream);
 }
 
 int nns_b200_topk_unpack(const uint64_t* d_keys, int m, int K, int* d_idx, float* d_dist, void* stream)

@@ -121,6 +121,10 @@ static inline cudaError_t stream_drain(cudaStream_t st)
 int search_keys_on(DeviceCtx* c, int k, int m, int n, const float* d_queries, const float* d_header,
                    const float* d_blocks, const float* d_section, int index_base, u64* d_keys, unsigned flags,
                    cudaStream_t st);
+// K nearest neighbours on device-resident data (d_section = NULL: FP32 kernel only)
+bool topk_wants_tensor(int k, int m, int n, unsigned flags);
+int topk_keys_on(DeviceCtx* c, int k, int m, int n, int K, const float* d_queries, const float* d_blocks, const float* d_section,
+                 int index_base, u64* d_keys, unsigned flags, cudaStream_t st);
 // does the planner put this search on the tcgen05 path (so that the caller builds a tensor section)?
 bool plan_wants_tensor(int k, int m, int n, unsigned flags, int num_sms);
 

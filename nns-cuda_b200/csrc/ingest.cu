@@ -510,13 +510,16 @@ int nns_b200_search_topk_host(int k, int m, int n, int K, const float* s_points,
     DeviceGuard guard;
     ST_TRY(guard.enter(c->device));
     const unsigned flags = host_flags();
-    const long long chunk = ingest_chunk_points(k, n, false);
+    // the tcgen05-screened search takes the whole set as one index (its sample pass fixes one threshold per query)
+    const bool tensor = topk_wants_tensor(k, m, n, flags);
+    const long long chunk = tensor ? std::max<long long>(LB, ((long long)n + LB - 1) / LB * LB) : ingest_chunk_points(k, n, false);
     const int nchunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
     const size_t bf = index_block_floats(k);
     const size_t cells = (size_t)m * K;
     ST_TRY(buf_reserve(&c->q, (size_t)m * k * sizeof(float)));
     ST_TRY(buf_reserve(&c->r, (size_t)n * k * sizeof(float)));
     ST_TRY(buf_reserve(&c->index, ((size_t)INDEX_HEADER_FLOATS + (size_t)ceil_div(n, LB) * bf) * sizeof(float)));
+    if (tensor) ST_TRY(buf_reserve(&c->tsec, tensor_section_floats(k, n) * sizeof(float)));
     ST_TRY(buf_reserve(&c->keys, cells * sizeof(u64)));
     ST_TRY(buf_reserve(&c->idx, cells * sizeof(int) * 2));
     ST_TRY(ctx_events(c, nchunks + 1));
@@ -538,16 +541,14 @@ int nns_b200_search_topk_host(int k, int m, int n, int K, const float* s_points,
         CU_TRY(cudaStreamWaitEvent(c->compute, c->events[ci], 0));
         float* d_blocks_c = d_index + INDEX_HEADER_FLOATS + (j0 / LB) * (long long)bf;
         CU_TRY(launch_index_build(k, cn, d_r + j0 * k, d_index, d_blocks_c, ci == 0, c->compute));
-        const int splits = topk_choose_splits(m, cn, c->num_sms);
-        u64* scratch = nullptr;
-        CU_TRY(cudaMallocFromPoolAsync((void**)&scratch, topk_scratch_bytes(m, K, splits), c->pool, c->compute));
-        int launches = 0;
-        const cudaError_t e = topk_search_launch(k, m, cn, K, d_q, d_blocks_c, (int)j0, d_keys, scratch, splits,
-                                                 (flags & NNS_B200_FLAG_V0_ROUNDING) != 0, c->compute, &launches);
-        count_launches(launches + 1);
-        const cudaError_t fe = cudaFreeAsync(scratch, c->compute);
-        CU_TRY(e);
-        CU_TRY(fe);
+        count_launches(1);
+        float* d_section = nullptr;
+        if (tensor) {
+            d_section = (float*)c->tsec.p;
+            CU_TRY(tensor_index_build(k, cn, d_index, d_blocks_c, d_section, c->compute));
+            count_launches(3);
+        }
+        ST_TRY(topk_keys_on(c, k, m, cn, K, d_q, d_blocks_c, d_section, (int)j0, d_keys, flags, c->compute));
     }
     if (nchunks == 0) {
         CU_TRY(cudaEventRecord(c->events[0], c->copy));

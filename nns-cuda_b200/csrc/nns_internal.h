@@ -79,8 +79,19 @@ constexpr int TOPK_MAX_K = 32;
 constexpr int TOPK_MAX_DIMS = 1024;
 int topk_choose_splits(int m, int n, int num_sms);
 size_t topk_scratch_bytes(int m, int K, int splits);
+// stride > 1 splits the reference blocks into a sample (b % stride == 0; only_sampled = 1) and the rest (0);
+// enable != NULL: a conditional launch that exits at once when *enable == 0
 cudaError_t topk_search_launch(int k, int m, int n, int K, const float* d_queries, const float* d_blocks, int index_base,
-                               u64* d_keys, u64* d_scratch, int splits, bool exact, cudaStream_t st, int* launches);
+                               u64* d_keys, u64* d_scratch, int splits, bool exact, cudaStream_t st, int* launches,
+                               int stride = 1, int only_sampled = 0, const int* enable = nullptr);
+cudaError_t topk_merge_var_launch(u64* d_keys, const u64* d_exact, const unsigned* d_count, int m, int K, unsigned cap,
+                                  const unsigned* skip_if_set, cudaStream_t st);
+// K nearest neighbours through the tcgen05 screen (tensor_search.cu): exact FP32 top-K over a block sample gives
+// every query a distance threshold, the screen keeps the 32-reference units that can hold anything below it,
+// their exact distances are merged into the sorted key lists; *launches = kernels launched
+cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_queries, const float* d_blocks, const float* d_section,
+                               int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
+                               int* launches, unsigned* d_stats);
 cudaError_t topk_unpack_launch(const u64* d_keys, int m, int K, int* d_idx, float* d_dist, cudaStream_t st);
 
 // lowk_inst_N.cu (N = (k-1)/2)

@@ -298,6 +298,7 @@ struct CandBuf {
     unsigned region_cap;   // multiple of 32
     unsigned common_cap;
     unsigned n_ctas;
+    unsigned fixed_threshold;  // K-nearest search: approx_min[q] is a FIXED threshold, never lowered by the screen
 };
 
 __device__ __forceinline__ void cand_emit(const CandBuf& cb, unsigned* s_count, const unsigned cta, const TensorCand& c)

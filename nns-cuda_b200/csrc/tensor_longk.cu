@@ -159,7 +159,7 @@ tensor_screen_longk_kernel(const unsigned char* __restrict__ qimage, const int m
                     TensorCand cnd;
                     cnd.q = (int)q; cnd.unit = unit0 + c; cnd.smin = cm;
                     cand_emit(cb, s_cand_count, cta, cnd);
-                    if (cm < run_min) {
+                    if (cm < run_min && !cb.fixed_threshold) {
                         run_min = cm;
                         thresh = run_min + my_band;
                         atomicMin(approx_min + q, f2ord(run_min));

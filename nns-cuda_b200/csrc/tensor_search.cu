@@ -516,7 +516,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 TensorCand cnd;
                 cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
                 cand_emit(cb, s_cand_count, cta, cnd);
-                if (cm < run_min) {
+                if (cm < run_min && !cb.fixed_threshold) {
                     run_min = cm;
                     thresh = run_min + my_band;
                     atomicMin(approx_min + q, f2ord(run_min));
@@ -555,7 +555,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     TensorCand cnd;
                     cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
                     cand_emit(cb, s_cand_count, cta, cnd);
-                    if (cm < run_min) {
+                    if (cm < run_min && !cb.fixed_threshold) {
                         run_min = cm;
                         thresh = run_min + my_band;
                         atomicMin(approx_min + q, f2ord(run_min));
@@ -641,7 +641,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     TensorCand cnd;
                     cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
                     cand_emit(cb, s_cand_count, cta, cnd);
-                    if (cm < run_min) {
+                    if (cm < run_min && !cb.fixed_threshold) {
                         run_min = cm;
                         thresh = run_min + my_band;
                         atomicMin(approx_min + q, f2ord(run_min));
@@ -705,7 +705,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                     TensorCand cnd;
                     cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
                     cand_emit(cb, s_cand_count, cta, cnd);
-                    if (cm < run_min) {
+                    if (cm < run_min && !cb.fixed_threshold) {
                         run_min = cm;
                         thresh = run_min + my_band;
                         atomicMin(approx_min + q, f2ord(run_min));
@@ -1265,6 +1265,253 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     if (launches) *launches = nl;
     cudaError_t e2 = cudaFreeAsync(scratch, st);
     return e != cudaSuccess ? e : e2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K nearest neighbours through the screen
+// ---------------------------------------------------------------------------------------------
+// The 1-NN screen keeps a unit when its minimum is within the band of the RUNNING minimum.  For the K nearest
+// the threshold must not move with the best reference, so it is fixed before the screen runs: an exact FP32
+// K-nearest pass (topk_search.cu) over a SAMPLE of the reference blocks (every TOPK_SAMPLE_STRIDE-th block)
+// leaves K true distances per query; the K-th, tau, is an upper bound of the final K-th distance, and a
+// reference can only belong to the answer if its V0-form distance is <= tau, i.e. if its approximate score
+// S~ <= tau - |q'|^2 + E.  The screen runs with that fixed threshold (CandBuf::fixed_threshold) over all blocks,
+// the re-score evaluates the candidate units exactly, skips the sampled blocks (already in the lists) and
+// appends every reference with d <= tau to a per-query list; topk_merge_var_kernel folds the lists into the
+// sorted keys.  Expected list length = K * stride for any data the sample represents; a list or the
+// candidate buffer that overflows raises the same device flag as in the 1-NN search and the FP32 K-nearest
+// kernel, launched behind the flag over the non-sampled blocks, finishes the job -- no host round trip.
+constexpr int TOPK_SAMPLE_STRIDE = 16;
+
+// amin[q] = tau(q) - |q'|^2 (ordered encoding); band[q] stays the 2E the query-image kernel wrote
+__global__ void tensor_topk_threshold_kernel(const float* __restrict__ queries, const int m, const int k, const float* __restrict__ hdr,
+                                             const u64* __restrict__ keys, const int K, unsigned* __restrict__ approx_min)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    float qn = 0.0f;
+    for (int t = 0; t < k; ++t) {
+        const float x = __fsub_rn(__ldg(queries + (size_t)q * k + t), hdr[t]);
+        qn = __fmaf_rn(x, x, qn);
+    }
+    const float tau = __uint_as_float((unsigned)(keys[(size_t)q * K + (K - 1)] >> 32));  // +INF while fewer than K are known
+    const float thr = tau - qn;  // NaN (INF - INF, NaN queries) compares false everywhere: nothing is screened in, tau = INF decides below
+    approx_min[q] = f2ord(thr == thr ? thr : inf_f());
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+tensor_rescore_topk_kernel(const float* __restrict__ queries, const int k, const float* __restrict__ blocks, const int index_base,
+                           const CandBuf cb, const u64* __restrict__ keys, const int K, u64* __restrict__ exact,
+                           unsigned* __restrict__ exact_count, const unsigned cap, const int stride)
+{
+    const unsigned common = *cb.common_count;
+    if (common > cb.common_cap || cb.status[1] != 0u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cb.status[1] = 1u;
+        return;
+    }
+    const int lane = (int)(threadIdx.x & 31);
+    const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const unsigned gpr = cb.region_cap / 32;
+    const unsigned region_groups = cb.n_ctas * gpr;
+    const unsigned groups = region_groups + (common + 31) / 32;
+    for (unsigned gi = wid; gi < groups; gi += nw) {
+        size_t first;
+        unsigned count;
+        if (gi < region_groups) {
+            const unsigned cta = gi / gpr, s0 = (gi - cta * gpr) * 32;
+            const unsigned used = cb.cta_count[cta];
+            if (s0 >= used) continue;
+            first = (size_t)cta * cb.region_cap + s0;
+            count = min(32u, used - s0);
+        } else {
+            const unsigned s0 = (gi - region_groups) * 32;
+            first = (size_t)cb.n_ctas * cb.region_cap + s0;
+            count = min(32u, common - s0);
+        }
+        TensorCand mine;
+        mine.q = 0; mine.unit = 0; mine.smin = 0.0f;
+        if ((unsigned)lane < count) mine = cb.rec[first + lane];
+        for (unsigned src = 0; src < count; ++src) {
+            const int cq = __shfl_sync(0xffffffffu, mine.q, (int)src);
+            const int unit = __shfl_sync(0xffffffffu, mine.unit, (int)src);
+            const int jl = unit * 32 + lane;
+            if (stride > 1 && ((jl >> 7) % stride) == 0) continue;  // a sampled block: its references are in the lists already (uniform)
+            const float* col = blocks + (size_t)(jl >> 7) * (k + 1) * LB + (jl & (LB - 1));
+            const float* qp = queries + (size_t)cq * k;
+            float d = 0.0f;
+            for (int tb = 0; tb < k; tb += 32) {
+                const float qv = (tb + lane < k) ? __ldg(qp + tb + lane) : 0.0f;
+                const int te = min(32, k - tb);
+#pragma unroll 8
+                for (int tt = 0; tt < te; ++tt) {
+                    const float qt = __shfl_sync(0xffffffffu, qv, tt);
+                    const float e = qt - __ldg(col + (size_t)(tb + tt) * LB);
+                    d = EXACT ? __fadd_rn(d, __fmul_rn(e, e)) : __fmaf_rn(e, e, d);
+                }
+            }
+            const float tau = __uint_as_float((unsigned)(keys[(size_t)cq * K + (K - 1)] >> 32));
+            const bool pass = d <= tau && d < inf_f();  // padding lanes are NaN
+            const unsigned pm = __ballot_sync(0xffffffffu, pass);
+            if (pm == 0u) continue;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(exact_count + cq, (unsigned)__popc(pm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned)__popc(pm) > cap) {
+                if (lane == 0) cb.status[1] = 1u;  // list full: the FP32 kernel launched behind the flag takes over
+                continue;
+            }
+            if (pass) exact[(size_t)cq * cap + base + (unsigned)__popc(pm & ((1u << lane) - 1u))] = pack_key(d, index_base + jl);
+        }
+    }
+}
+
+cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_queries, const float* d_blocks, const float* d_section,
+                               int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
+                               int* launches, unsigned* d_stats)
+{
+    const TensorGeom g = tensor_geom(k);
+    const TensorGeom gp = tensor_geom(k, true);
+    const bool modes = tensor_has_modes(k);
+    const unsigned* mode_word = modes ? reinterpret_cast<const unsigned*>(d_section) + THDR_MODE : nullptr;
+    const int nblocks = (n + LB - 1) / LB;
+    const bool longk = g.KB > 2;
+    const int rows = longk ? tensor_longk_rows(g.KB) : T_BM;
+    const int strips = (m + rows - 1) / rows;
+    const float* hdr = d_section;
+    const unsigned char* rimage = reinterpret_cast<const unsigned char*>(d_section + TENSOR_HDR_FLOATS);
+    const int stride = TOPK_SAMPLE_STRIDE;
+    int nl = 0;
+
+    // 1. exact K nearest over the block sample -> tau per query
+    const int splits_s = topk_choose_splits(m, (nblocks / stride + 1) * LB, num_sms);
+    u64* sample_scratch = nullptr;
+    cudaError_t e = pool ? cudaMallocFromPoolAsync((void**)&sample_scratch, topk_scratch_bytes(m, K, splits_s), pool, st)
+                         : cudaMallocAsync((void**)&sample_scratch, topk_scratch_bytes(m, K, splits_s), st);
+    if (e != cudaSuccess) return e;
+    int l2 = 0;
+    e = topk_search_launch(k, m, n, K, d_queries, d_blocks, index_base, d_keys, sample_scratch, splits_s, exact, st, &l2, stride, 1, nullptr);
+    nl += l2;
+    cudaError_t fe = cudaFreeAsync(sample_scratch, st);
+    if (e != cudaSuccess) return e;
+    if (fe != cudaSuccess) return fe;
+
+    // 2. the screen with the fixed threshold, in query batches (as tensor_search; at most 1 GiB of exact lists per batch)
+    const size_t per_strip_exact = (size_t)rows * (size_t)(stride * K + (int)(6.0 * stride * sqrt((double)K)) + 64) * sizeof(u64);
+    const int max_batch_ctas = (int)std::max<size_t>((size_t)num_sms, std::min<size_t>((size_t)4 * num_sms, ((size_t)1 << 30) / per_strip_exact));
+    int batch_strips = strips, nbatches = 1;
+    if (strips > max_batch_ctas) {
+        nbatches = (strips + max_batch_ctas - 1) / max_batch_ctas;
+        batch_strips = (strips + nbatches - 1) / nbatches;
+        batch_strips = std::min(max_batch_ctas, (batch_strips + num_sms - 1) / num_sms * num_sms);
+        nbatches = (strips + batch_strips - 1) / batch_strips;
+    }
+    int splits = 1;
+    {
+        double best = 1e300;
+        for (int sp = 1; sp <= std::min(nblocks, 64); ++sp) {
+            const int t = (nblocks + sp - 1) / sp;
+            const int se = (nblocks + t - 1) / t;
+            const double waves = (double)(((long long)batch_strips * se + num_sms - 1) / num_sms);
+            const double cost = waves * ((double)t + 24.0);
+            if (cost < best * 0.97) { best = cost; splits = se; }
+        }
+    }
+    const int tps = (nblocks + splits - 1) / splits;
+    splits = (nblocks + tps - 1) / tps;
+    CandBuf cb{};
+    cb.fixed_threshold = 1u;
+    cb.n_ctas = (unsigned)batch_strips * (unsigned)splits;
+    const size_t batch_queries = (size_t)batch_strips * rows;
+    // exact candidates per query: the references below the K-th SAMPLED one number K (stride - 1) on average with a
+    // standard deviation of ~stride sqrt(K) (negative binomial); mean + 6 sigma
+    const unsigned cap = (unsigned)(stride * K + (int)(6.0 * stride * sqrt((double)K)) + 64);
+    const size_t exact_bytes = batch_queries * cap * sizeof(u64);
+    {
+        const size_t budget = tensor_record_budget() / 2;  // the other half of the scratch budget holds the exact lists
+        const size_t common = std::min<size_t>(batch_queries * 64 + 65536, budget / 4);
+        size_t region = ((budget - common) / cb.n_ctas) & ~(size_t)31;
+        region = std::max<size_t>((size_t)rows * 64, std::min<size_t>((size_t)rows * 1024, region));
+        cb.region_cap = (unsigned)region;
+        cb.common_cap = (unsigned)common;
+    }
+    const size_t cand_records = (size_t)cb.n_ctas * cb.region_cap + cb.common_cap;
+    const size_t qimg_bytes = (size_t)batch_strips * image_bytes(rows, g.KB, g.KS);
+    const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
+    const size_t off_amin = off_band + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_cnt = off_amin + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_ccnt = off_cnt + (((size_t)nbatches * 4 + 255) & ~(size_t)255);
+    const size_t off_ecnt = off_ccnt + (((size_t)cb.n_ctas * 4 + 255) & ~(size_t)255);
+    const size_t off_exact = off_ecnt + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_cand = off_exact + ((exact_bytes + 255) & ~(size_t)255);
+    const size_t total = off_cand + cand_records * sizeof(TensorCand);
+    unsigned char* scratch = nullptr;
+    e = pool ? cudaMallocFromPoolAsync((void**)&scratch, total, pool, st) : cudaMallocAsync((void**)&scratch, total, st);
+    if (e != cudaSuccess) return e;
+    float* band = reinterpret_cast<float*>(scratch + off_band);
+    unsigned* amin = reinterpret_cast<unsigned*>(scratch + off_amin);
+    unsigned* common_counts = reinterpret_cast<unsigned*>(scratch + off_cnt);
+    unsigned* exact_count = reinterpret_cast<unsigned*>(scratch + off_ecnt);
+    u64* exact_list = reinterpret_cast<u64*>(scratch + off_exact);
+    cb.cta_count = reinterpret_cast<unsigned*>(scratch + off_ccnt);
+    cb.rec = reinterpret_cast<TensorCand*>(scratch + off_cand);
+    cb.status = d_stats;
+    tensor_status_init_kernel<<<(nbatches + 255) / 256, 256, 0, st>>>(d_stats, (unsigned)std::min<size_t>(cand_records, 0xffffffffu), common_counts,
+                                                                      nbatches, mode_word, (unsigned)(g.KB * 64 + g.KS * 16),
+                                                                      (unsigned)(gp.KB * 64 + gp.KS * 16));
+    e = cudaGetLastError();
+    nl += 1;
+    const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
+    const size_t smem_plain = std::max(tensor_smem_bytes(gp), (size_t)120 * 1024);
+    for (int b = 0; b < nbatches && e == cudaSuccess; ++b) {
+        const int s0 = b * batch_strips;
+        const int bs = std::min(batch_strips, strips - s0);
+        const long long q0 = (long long)s0 * rows;
+        const int bm = (int)std::min<long long>((long long)bs * rows, (long long)m - q0);
+        const float* bq = d_queries + (size_t)q0 * k;
+        u64* bkeys = d_keys + (size_t)q0 * K;
+        cb.common_count = common_counts + b;
+        cb.n_ctas = (unsigned)bs * (unsigned)splits;
+        dim3 grid((unsigned)bs, (unsigned)splits);
+        e = cudaMemsetAsync(exact_count, 0, (size_t)bm * 4, st);
+        if (e != cudaSuccess) break;
+        tensor_query_image_kernel<<<bs, rows, 0, st>>>(bq, bm, k, g, hdr, scratch, band, amin, mode_word, 0u);
+        if (modes) tensor_query_image_kernel<<<bs, rows, 0, st>>>(bq, bm, k, gp, hdr, scratch, band, amin, mode_word, 1u);
+        tensor_topk_threshold_kernel<<<(bm + 255) / 256, 256, 0, st>>>(bq, bm, k, hdr, bkeys, K, amin);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
+        if (longk) e = tensor_longk_launch(g.KB, grid, st, scratch, bm, rimage, nblocks, tps, band, amin, cb);
+        else e = tensor_screen_dispatch(g, grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 0u);
+        if (e == cudaSuccess && modes)
+            e = tensor_screen_dispatch(gp, grid, smem_plain, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 1u);
+        if (e != cudaSuccess) break;
+        const int rgrid = num_sms * 8;
+        if (exact)
+            tensor_rescore_topk_kernel<true><<<rgrid, 256, 0, st>>>(bq, k, d_blocks, index_base, cb, bkeys, K, exact_list, exact_count, cap, stride);
+        else
+            tensor_rescore_topk_kernel<false><<<rgrid, 256, 0, st>>>(bq, k, d_blocks, index_base, cb, bkeys, K, exact_list, exact_count, cap, stride);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
+        // the lists of this batch into its keys -- unless something overflowed (then nothing of the screen is used)
+        e = topk_merge_var_launch(bkeys, exact_list, exact_count, bm, K, cap, d_stats + 1, st);
+        nl += modes ? 7 : 5;
+    }
+    fe = cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return e;
+    if (fe != cudaSuccess) return fe;
+    // 3. fallback behind the overflow flag: exact FP32 K nearest over the NON-sampled blocks (the sample is in the keys;
+    //    batches merged before the overflow only hold true K-nearest candidates, which the merge keeps or replaces)
+    const int splits_f = topk_choose_splits(m, n, num_sms);
+    u64* fb_scratch = nullptr;
+    e = pool ? cudaMallocFromPoolAsync((void**)&fb_scratch, topk_scratch_bytes(m, K, splits_f), pool, st)
+             : cudaMallocAsync((void**)&fb_scratch, topk_scratch_bytes(m, K, splits_f), st);
+    if (e != cudaSuccess) return e;
+    e = topk_search_launch(k, m, n, K, d_queries, d_blocks, index_base, d_keys, fb_scratch, splits_f, exact, st, &l2, stride, 0,
+                           reinterpret_cast<const int*>(d_stats + 1));
+    nl += l2;
+    fe = cudaFreeAsync(fb_scratch, st);
+    if (launches) *launches = nl;
+    return e != cudaSuccess ? e : fe;
 }
 
 }  // namespace nns

@@ -33,11 +33,14 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v)
     return v;
 }
 
-// insert `key` into the list held one entry per lane (lanes >= K hold 0 and are never the maximum);
-// returns the new worst key
-__device__ __forceinline__ u64 topk_insert(u64& mine, const u64 key, const u64 worst, const int lane)
+// insert `key` into the list held one entry per lane (in_list = lane < K; the other lanes hold 0 and are never the
+// maximum); returns the new worst key
+__device__ __forceinline__ u64 topk_insert(u64& mine, const u64 key, const u64 worst, const int lane, const bool in_list)
 {
     if (key < worst) {
+        // a key that is already in the list (the same reference offered twice: overlapping shards, or the FP32 pass
+        // that finishes a tensor-screened search whose first batches were merged already) is not inserted again
+        if (__any_sync(0xffffffffu, in_list && mine == key)) return worst;
         const unsigned holders = __ballot_sync(0xffffffffu, mine == worst);
         if (lane == __ffs(holders) - 1) mine = key;
         return warp_max_u64(mine);
@@ -49,9 +52,13 @@ template <bool EXACT>
 __global__ void __launch_bounds__(TOPK_THREADS)
 topk_search_kernel(const float* __restrict__ queries, const int m, const int k, const int K,
                    const float* __restrict__ blocks, const int nblocks, const int blocks_per_split,
-                   const int index_base, u64* __restrict__ lists /* [splits][m][K] */)
+                   const int index_base, u64* __restrict__ lists /* [splits][m][K] */,
+                   const int stride, const int only_sampled, const int* __restrict__ enable)
 {
+    // stride > 1: the reference blocks are partitioned into the SAMPLED ones (b % stride == 0) and the rest;
+    // only_sampled = 1 scans the sample, 0 the rest (the tensor-screened K-nearest search: tensor_topk_search)
     extern __shared__ __align__(16) float qs[];  // [TOPK_WARPS][k][TOPK_WQ]
+    if (enable != nullptr && *enable == 0) return;  // conditional fallback launch
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     const int q0 = (int)blockIdx.x * TOPK_CTA_Q + warp * TOPK_WQ;
     float* wq = qs + (size_t)warp * k * TOPK_WQ;
@@ -73,6 +80,7 @@ topk_search_kernel(const float* __restrict__ queries, const int m, const int k, 
     const int b0 = (int)blockIdx.y * blocks_per_split;
     const int b1 = min(nblocks, b0 + blocks_per_split);
     for (int b = b0; b < b1; ++b) {
+        if (stride > 1 && ((b % stride == 0) != (only_sampled != 0))) continue;
         const float4* blk = reinterpret_cast<const float4*>(blocks + (size_t)b * (k + 1) * LB) + lane;
         float acc[4][TOPK_WQ];
 #pragma unroll
@@ -109,7 +117,7 @@ topk_search_kernel(const float* __restrict__ queries, const int m, const int k, 
                     const float d = __shfl_sync(0xffffffffu, acc[e][i], src);
                     if ((h >> e) & 1u) {  // uniform
                         const u64 key = (d < inf_f()) ? pack_key(d, index_base + b * LB + 4 * src + e) : KEY_INIT;
-                        worst[i] = topk_insert(mine[i], key, worst[i], lane);
+                        worst[i] = topk_insert(mine[i], key, worst[i], lane, lane < K);
                     }
                 }
                 tau[i] = __uint_as_float((unsigned)(worst[i] >> 32));
@@ -121,11 +129,51 @@ topk_search_kernel(const float* __restrict__ queries, const int m, const int k, 
         if (q0 + i < m && lane < K) lists[((size_t)blockIdx.y * m + (q0 + i)) * K + lane] = mine[i];
 }
 
+// merge of variable-length candidate lists (tensor-screened K-nearest search): exact[q][0 .. count[q]) into keys[q]
+__global__ void __launch_bounds__(256)
+topk_merge_var_kernel(u64* __restrict__ keys, const u64* __restrict__ exact, const unsigned* __restrict__ count, const int m,
+                      const int K, const unsigned cap, const unsigned* __restrict__ skip_if_set)
+{
+    if (skip_if_set != nullptr && *skip_if_set != 0u) return;  // the screen overflowed: the FP32 pass launched next decides
+    const int lane = (int)(threadIdx.x & 31);
+    const int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (q >= m) return;
+    u64 mine = lane < K ? keys[(size_t)q * K + lane] : 0ull;
+    u64 worst = warp_max_u64(mine);
+    const unsigned cnt = min(count[q], cap);
+    for (unsigned i0 = 0; i0 < cnt; i0 += 32) {
+        const u64 cand = (i0 + lane < cnt) ? exact[(size_t)q * cap + i0 + lane] : KEY_INIT;
+        unsigned live = __ballot_sync(0xffffffffu, cand < worst);
+        while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            const u64 key = __shfl_sync(0xffffffffu, cand, src);
+            worst = topk_insert(mine, key, worst, lane, lane < K);
+        }
+    }
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+        const u64 o = __shfl_sync(0xffffffffu, mine, j);
+        rank += (o < mine || (o == mine && j < lane)) ? 1 : 0;
+    }
+    if (lane < K) keys[(size_t)q * K + rank] = mine;
+}
+
+cudaError_t topk_merge_var_launch(u64* d_keys, const u64* d_exact, const unsigned* d_count, int m, int K, unsigned cap,
+                                  const unsigned* skip_if_set, cudaStream_t st)
+{
+    if (m == 0) return cudaSuccess;
+    topk_merge_var_kernel<<<(unsigned)(((long long)m * 32 + 255) / 256), 256, 0, st>>>(d_keys, d_exact, d_count, m, K, cap, skip_if_set);
+    return cudaGetLastError();
+}
+
 // one warp per query: the K smallest keys of (keys[q][0..K) as given) U (lists[s][q][0..K) for every split),
 // written back to keys[q] in ascending order
 __global__ void __launch_bounds__(256)
-topk_merge_kernel(u64* __restrict__ keys, const u64* __restrict__ lists, const int m, const int K, const int splits)
+topk_merge_kernel(u64* __restrict__ keys, const u64* __restrict__ lists, const int m, const int K, const int splits,
+                  const int* __restrict__ enable)
 {
+    if (enable != nullptr && *enable == 0) return;  // the search behind this merge did not run
     const int lane = (int)(threadIdx.x & 31);
     const int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (q >= m) return;
@@ -139,7 +187,7 @@ topk_merge_kernel(u64* __restrict__ keys, const u64* __restrict__ lists, const i
             const int src = __ffs(live) - 1;
             live &= live - 1;
             const u64 key = __shfl_sync(0xffffffffu, cand, src);
-            worst = topk_insert(mine, key, worst, lane);
+            worst = topk_insert(mine, key, worst, lane, lane < K);
         }
     }
     // rank = number of entries that sort before mine (KEY_INIT pads tie: break by lane)
@@ -183,7 +231,8 @@ int topk_choose_splits(int m, int n, int num_sms)
 }
 
 cudaError_t topk_search_launch(int k, int m, int n, int K, const float* d_queries, const float* d_blocks, int index_base,
-                               u64* d_keys, u64* d_scratch, int splits, bool exact, cudaStream_t st, int* launches)
+                               u64* d_keys, u64* d_scratch, int splits, bool exact, cudaStream_t st, int* launches,
+                               int stride, int only_sampled, const int* enable)
 {
     if (launches) *launches = 0;
     if (m == 0 || n == 0) return cudaSuccess;
@@ -196,15 +245,17 @@ cudaError_t topk_search_launch(int k, int m, int n, int K, const float* d_querie
     if (exact) {
         e = cudaFuncSetAttribute(topk_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        topk_search_kernel<true><<<grid, TOPK_THREADS, smem, st>>>(d_queries, m, k, K, d_blocks, nblocks, bps, index_base, d_scratch);
+        topk_search_kernel<true><<<grid, TOPK_THREADS, smem, st>>>(d_queries, m, k, K, d_blocks, nblocks, bps, index_base, d_scratch,
+                                                                   stride, only_sampled, enable);
     } else {
         e = cudaFuncSetAttribute(topk_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        topk_search_kernel<false><<<grid, TOPK_THREADS, smem, st>>>(d_queries, m, k, K, d_blocks, nblocks, bps, index_base, d_scratch);
+        topk_search_kernel<false><<<grid, TOPK_THREADS, smem, st>>>(d_queries, m, k, K, d_blocks, nblocks, bps, index_base, d_scratch,
+                                                                    stride, only_sampled, enable);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    topk_merge_kernel<<<(unsigned)(((long long)m * 32 + 255) / 256), 256, 0, st>>>(d_keys, d_scratch, m, K, splits);
+    topk_merge_kernel<<<(unsigned)(((long long)m * 32 + 255) / 256), 256, 0, st>>>(d_keys, d_scratch, m, K, splits, enable);
     if (launches) *launches = 2;
     return cudaGetLastError();
 }

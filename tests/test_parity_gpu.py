@@ -725,3 +725,55 @@ def test_long_contraction_adversarial(nns, oracle, torch_mod):
         v, _ = oracle.v0_omp(k, m, n, a, b)
         g = nns.DeviceIndex(dev(torch, b)).search(dev(torch, a), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
         assert np.array_equal(g, v), (name, int((g != v).sum()), nns.tensor_stats())
+
+
+# ---- K nearest neighbours through the tcgen05 screen ------------------------------------------------
+@pytest.mark.parametrize("kind,k,m,n,K", [("uniform", 3, 2048, 200_000, 8), ("clustered", 3, 3000, 300_000, 16), ("uniform", 16, 1024, 100_000, 32),
+                                          ("uniform", 128, 512, 50_000, 5), ("grid", 3, 700, 60_000, 1), ("uniform", 200, 300, 20_000, 4)])
+def test_topk_on_the_tensor_screen_matches_the_oracle(nns, oracle, torch_mod, kind, k, m, n, K):
+    """nns_b200_topk_keys with the tcgen05 screen forced: exact FP32 K-nearest over a block sample fixes a distance
+    threshold per query, the screen keeps the 32-reference units that can hold anything below it, their exact
+    distances are merged into the sorted lists.  With V0 rounding the lists must equal the oracle's exactly --
+    duplicates, grids and K = 1 (= V0) included -- and must not depend on shards or on the FP32 kernel."""
+    torch = torch_mod
+    s, r = make_case(kind, k, m, n, 101)
+    want_i, want_d = oracle.v0_topk(k, m, n, K, s, r)
+    index = nns.DeviceIndex(dev(torch, r))
+    gi, gd = index.topk(dev(torch, s), K, nns.FLAG_V0_ROUNDING | nns.FLAG_FORCE_TENSOR)
+    st = nns.tensor_stats()
+    gi, gd = gi.cpu().numpy(), gd.cpu().numpy()
+    assert np.array_equal(gi, want_i), (int((gi != want_i).sum()), st)
+    assert np.array_equal(gd, want_d)
+    assert st["overflow"] == 0, st
+    fi, _ = index.topk(dev(torch, s), K, nns.FLAG_V0_ROUNDING | nns.FLAG_FORCE_LOWK)
+    assert np.array_equal(fi.cpu().numpy(), gi)
+    # offering the same references twice does not duplicate entries (idempotent merge)
+    keys = index.topk_keys(dev(torch, s), K, None, nns.FLAG_V0_ROUNDING | nns.FLAG_FORCE_TENSOR)
+    keys = index.topk_keys(dev(torch, s), K, keys, nns.FLAG_V0_ROUNDING | nns.FLAG_FORCE_LOWK)
+    assert np.array_equal((keys.cpu().numpy().astype(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64), want_i)
+    if K == 1:
+        assert np.array_equal(gi[:, 0], oracle.v0_omp(k, m, n, s, r)[0])
+
+
+def test_topk_tensor_screen_overflow_hands_over_to_the_fp32_kernel(nns, oracle, torch_mod):
+    """All references identical: every unit is inside every threshold, the candidate buffer / lists overflow, and the
+    FP32 K-nearest kernel launched behind the device flag must finish the search (lowest indices win the ties)."""
+    torch = torch_mod
+    k, m, n, K = 3, 600, 40_000, 8
+    s, r = make_case("uniform", k, m, n, 103)
+    r = np.tile(r[:1], (n, 1))
+    want_i, want_d = oracle.v0_topk(k, m, n, K, s, r)
+    gi, gd = nns.DeviceIndex(dev(torch, r)).topk(dev(torch, s), K, nns.FLAG_V0_ROUNDING | nns.FLAG_FORCE_TENSOR)
+    assert nns.tensor_stats()["overflow"] == 1
+    assert np.array_equal(gi.cpu().numpy(), want_i) and np.array_equal(gd.cpu().numpy(), want_d)
+
+
+def test_topk_host_abi_plans_the_tensor_screen_for_large_problems(nns, oracle):
+    k, m, n, K = 3, 8192, 600_000, 8  # 4.9e9 pairs
+    s, r = make_case("uniform", k, m, n, 105)
+    sample = np.random.default_rng(3).permutation(m)[:256]
+    want_i, want_d = oracle.v0_topk(k, 256, n, K, s[sample], r)
+    hi, hd = nns.search_topk_host(k, m, n, K, s, r)
+    assert nns.tensor_stats()["kp"] == 16  # the screen ran
+    assert (hi[sample] != want_i).mean() < 0.01  # FMA rounding may swap near-ties
+    np.testing.assert_allclose(hd[sample], want_d, rtol=2e-6)
