@@ -290,16 +290,20 @@ def roofline_of(nns_b200, name, k, m, nloc, flags, kern_ms_avg, clocks, world, t
         # (ONE minimum per pair in the TMEM epilogue: priced by executed lane-slots) and the tensor
         # pipe (algorithmic 2k FLOPs per pair; the hi/lo column triples and padding are real MMA work but
         # count as zero -- `tensor_frac_executed` shows them).  `bound` = the one with the higher utilisation.
-        kp = (tstats or {}).get("kp") or nns_b200.tensor_kp(k)  # the precision mode the index chose (split or plain BF16 columns)
-        alu_frac = rate * 1.0 / lane_peak
+        kp = (tstats or {}).get("kp") or nns_b200.tensor_kp(k)  # the precision mode the index chose (split BF16 or plain F16 columns)
+        f16 = (tstats or {}).get("mode") == "f16"
+        # FP32 accumulators: FMNMX3 retires two values per instruction at half the FP32 lane rate = 1 lane-slot per pair;
+        # F16 accumulators: HMNMX2 / VHMNMX retire two (four) values at the full (half) rate = 0.5 lane-slots per pair
+        slots = 0.5 if f16 else 1.0
+        alu_frac = rate * slots / lane_peak
         tensor_frac = rate * 2.0 * k / 1e12 / bf16_peak
         tensor_exec = rate * 2.0 * kp / 1e12 / bf16_peak
-        kernel = "tcgen05 %s BF16 screen (K = %d columns for k = %d) + query image + exact FP32 re-score" % (
-            "split-precision" if kp >= 3 * k else "plain", kp, k)
+        kernel = "tcgen05 %s screen (K = %d columns for k = %d) + query image + exact FP32 re-score" % (
+            "plain F16 (F16 accumulators)" if f16 else ("split-precision BF16" if kp >= 3 * k else "plain BF16"), kp, k)
         if alu_frac >= tensor_exec:
-            roofline = {"bound": "fp32", "achieved": rate * 2.0 / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": alu_frac,
-                        "kernel": kernel + "; bound by one FMNMX3 lane-slot per pair in the TMEM epilogue",
-                        "executed_lane_slots_per_pair": 1, "peak_source": fp32_src + "; the ALU-pipe lane rate equals the FP32 lane rate"}
+            roofline = {"bound": "fp32", "achieved": rate * 2.0 * slots / 1e12, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": alu_frac,
+                        "kernel": kernel + "; bound by %s lane-slot per pair in the TMEM epilogue" % ("half an HMNMX2" if f16 else "one FMNMX3"),
+                        "executed_lane_slots_per_pair": slots, "peak_source": fp32_src + "; the ALU-pipe lane rate equals the FP32 lane rate"}
         else:
             roofline = {"bound": "tensor", "achieved": rate * 2.0 * k / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tensor_frac,
                         "kernel": kernel + "; bound by the tensor pipe, which executes %.1fx the algorithmic FLOPs" % (kp / k),
@@ -310,7 +314,8 @@ def roofline_of(nns_b200, name, k, m, nloc, flags, kern_ms_avg, clocks, world, t
         achieved = rate * 2.0 * k / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
                     "peak_source": f"{pk_src} bf16_tflops (burst, cuBLAS 8192^3)",
-                    "kernel": "tcgen05 BF16 screen (K = %d columns) + query image + exact FP32 re-score" % nns_b200.tensor_kp(k)}
+                    "kernel": "tcgen05 %s screen (K = %d columns) + query image + exact FP32 re-score" % (
+                        "F16 (F16 accumulators)" if (tstats or {}).get("mode") == "f16" else "BF16", nns_b200.tensor_kp(k))}
         if pk.get("bf16_tflops_sustained"):
             roofline["frac_of_sustained_peak"] = achieved / float(pk["bf16_tflops_sustained"])
     else:

@@ -12,8 +12,10 @@ namespace nns {
 // [THDR_FLAGS] bit 0: unusable; [THDR_PART_MAX + g], [THDR_PART_FLAGS + g] per-GPU partials (multi-GPU ingest)
 constexpr int MAX_PEERS = 8;
 constexpr int HDR_PART_MAX = 8;
-constexpr int THDR_MAX = 512, THDR_FLAGS = 513, THDR_MODE = 515, THDR_PART_MAX = 520, THDR_PART_FLAGS = 536;
-// [THDR_MODE] 0 = split-precision operand images, 1 = plain BF16 (only for TENSOR_PLAIN_MIN_K <= k <= TENSOR_SPLIT_MAX_K)
+constexpr int THDR_MAX = 512, THDR_FLAGS = 513, THDR_MODE = 515, THDR_SCALE = 517, THDR_PART_MAX = 520, THDR_PART_FLAGS = 536;
+// [THDR_MODE] 0 = the default BF16 operand images (split precision up to TENSOR_SPLIT_MAX_K, plain above), 2 = plain F16 operands
+// with F16 accumulators (TENSOR_PLAIN_MIN_K <= k <= 128, chosen per index by tensor_index_build); [THDR_SCALE] its reference scale
+constexpr unsigned TMODE_DEFAULT = 0u, TMODE_F16 = 2u;
 struct BlockDsts { float* p[MAX_PEERS]; int count; };            // first block of the part in every destination index
 struct ImageDsts { unsigned char* p[MAX_PEERS]; int count; };    // first tile image of the part in every destination
 struct HeaderPeers { float* header[MAX_PEERS]; float* section[MAX_PEERS]; int count; int self; };

@@ -3,6 +3,7 @@
 // mbarrier wrappers, UMMA descriptors, operand-image geometry, the error bound and the candidate buffer.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "nns_internal.h"
 
@@ -24,12 +25,21 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #ifndef NNS_T_SPIN
 #define NNS_T_SPIN 2        // bit 0: the epilogue warps poll their mbarrier, bit 1: the MMA issuer polls
 #endif
+#ifndef NNS_T_SPIN_F16
+#define NNS_T_SPIN_F16 0    // the same for the F16 screens: three polling issuers cost more (power-capped clock) than their wake-up saves
+#endif
 #ifndef NNS_T_PIPE
 #define NNS_T_PIPE 2        // epilogue of the 64-reference units: 0 = one unit per loop trip, a candidate test per 32-column chunk;
 #endif                      // 2 = NNS_T_TRIP units per trip and ONE test per trip (12 % faster on C2: profiles/r2_tune_trip.txt);
                             // 1 = additionally two rotating 32-column register sets with a load in flight under every reduction (slower)
 #ifndef NNS_T_ISS
 #define NNS_T_ISS 2         // MMA-issuing threads of the short-contraction screens (k <= 9, plain mid-k): 1 or 2
+#endif
+#ifndef NNS_T_ISS_F16
+#define NNS_T_ISS_F16 3     // the same for the F16-accumulator variants: 3 = A in TMEM, three buffers, one issuer each; 2 / 4 = SS form, four buffers
+#endif
+#ifndef NNS_T_TEAMS_F16
+#define NNS_T_TEAMS_F16 3   // epilogue teams of the F16 short-contraction screen (NNS_T_ISS_F16 = 3): 2 or 3
 #endif
 #ifndef NNS_T_TRIP
 #define NNS_T_TRIP 2        // NNS_T_PIPE = 2: units per loop trip / candidate test
@@ -128,6 +138,33 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64])
         : "r"(taddr)
         : "memory");
 }
+// 64 columns of 16-bit accumulators (F16 accumulators occupy the low half of their 32-bit cell), two per register:
+// register i = columns 2i (low half) and 2i + 1 (high half)
+__device__ __forceinline__ void tmem_ld64_pack16(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t hmin2(uint32_t a, uint32_t b)  // HMNMX2: per-half minimum, NaN loses
+{
+    uint32_t d;
+    asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ float hmin2_to_float(uint32_t a)  // the smaller half, exactly, as FP32
+{
+    float lo, hi;
+    asm("{.reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(lo), "=f"(hi) : "r"(a));
+    return fminf(lo, hi);
+}
 // true in exactly one (the lowest active) lane of the warp; must be called with all 32 lanes converged
 __device__ __forceinline__ bool elect_one_sync()
 {
@@ -211,13 +248,15 @@ __device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
+template <int SPIN = NNS_T_SPIN>
 __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity)  // epilogue
 {
-    if (NNS_T_SPIN & 1) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity);
+    if (SPIN & 1) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity);
 }
+template <int SPIN = NNS_T_SPIN>
 __device__ __forceinline__ void mbar_wait_mma(uint32_t bar, uint32_t parity)  // MMA issuer
 {
-    if (NNS_T_SPIN & 2) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity);
+    if (SPIN & 2) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity);
 }
 
 // byte offset of element (row, t) inside an operand image with `rows` rows:
@@ -264,20 +303,71 @@ __device__ __forceinline__ bool tensor_mode_mismatch(const unsigned* __restrict_
     return mode_word != nullptr && *reinterpret_cast<const volatile unsigned*>(mode_word) != my_mode;
 }
 
-// E(q) >= |S~ - S| + |d_V0 - D'| for every reference (see the file header), a = |q'|, rmax = max |r'|:
-//   operand rounding: plain BF16 2^-7 (1 + 2^-9) a rmax; split precision drops only ql.rl and the
-//   second-order remainders: 2 * 3.1 * 2^-18 a rmax.  The MMA's FP32 accumulation is charged 2^-21 per
-//   term (truncating adders); FP32 |r'|^2 and its 3-term split (KP + 5) 2^-24 rmax^2; centring and V0's
-//   own rounding (KP + 8) 2^-24 (a + rmax)^2; 5 % on top.
+// E(q) >= |S~ - S| + |d_V0 - D'| for every reference (see the file header), a = |q'|, rmax = max |r'|.
+// BF16 keeps 8 significant bits: unit roundoff u = 2^-8 (round to nearest).
+//   operand rounding, plain: each product (-2 q'_i)(r'_i) is off by <= (2u + u^2) of itself, the sum by
+//   <= (2u + u^2) * 2 a rmax = 2^-6 (1 + 2^-9) a rmax;  split precision: x = xh + xl + ex with |xl| <= u (1 + u) |x|,
+//   |ex| <= u^2 |x|; the MMA accumulates xh.yh + xh.yl + xl.yh, i.e. drops xl.yl + ex.y + (x - ex).ey
+//   <= 3 u^2 (1 + 2u) |x_i| |y_i|, summed <= 3.03 * 2^-16 * 2 a rmax.
+//   The MMA's FP32 accumulation is charged 2^-21 per term (truncating adders); FP32 |r'|^2 and its 3-term
+//   split (KP + 5) 2^-24 rmax^2; centring and V0's own rounding (KP + 8) 2^-24 (a + rmax)^2; 5 % on top.
 __host__ __device__ inline float tensor_error_bound(bool split, int KP, float a, float rmax)
 {
     const float u24 = 5.9604645e-8f;
-    const float c_round = split ? 6.2f * 3.8146973e-6f : 0.0078125f * 1.002f;
+    const float c_round = split ? 6.06f * 1.5258789e-5f : 0.015625f * 1.002f;
     const float E = (c_round + (float)KP * 2.04f * 4.7683716e-7f) * a * rmax + (KP + 5) * u24 * rmax * rmax +
                     (KP + 8) * u24 * (a + rmax) * (a + rmax);
     return E * 1.05f;
 }
 
+// ---- F16 mode (THDR_MODE = TMODE_F16): F16 operands AND F16 accumulators ----
+// The epilogue of the short contractions is bound by the ALU pipe: one FMNMX3 retires two new FP32 values at
+// 2 warp-instructions/clk/SM.  HMNMX2 retires two new F16 values at 4 warp-instructions/clk/SM
+// (tools/ubench_f16acc.cu, profiles/r2d_ubench_f16acc.txt), and tcgen05.ld ... pack::16b delivers an F16
+// accumulator tile two columns per register -- twice the reduction rate and half the registers.  F16 has 11
+// significant bits (u = 2^-11) but only 5 exponent bits, so the operands are scaled by powers of two:
+//   references  s r'        |r'|^2 column: s^2 |r'|^2 (three F16 terms)        s: per index (THDR_SCALE),
+//   queries    -2 t s q'    norm columns:  t                                   t: per query
+// and the accumulator holds u_q S~ with u_q = t s^2 (kept per query; every comparison happens in unscaled FP32
+// units).  s brings the SAMPLED radius of the reference cloud to [4, 8) (the exact maximum is only known once
+// the images exist); an index whose true radius R = s rmax exceeds F16_R_MAX is flagged unusable (band = INF ->
+// FP32 fallback), i.e. the sample may under-estimate the radius 22x.  t = the largest power of two <= 2^8 with
+// t R (R + 2A) <= 2^15 and 2 t A <= 2^15 (A = s a): no operand and no partial sum can overflow; t < 2^-14
+// (a query 2^20 cloud radii away) makes that query unusable.
+// Error: operand rounding (2u + u^2) * 2 a rmax = 2^-9 (1 + 2^-12) a rmax; every MMA instruction rounds the running
+// sum to F16 (measured: round to nearest; charged u (1 + 2^-6) of the largest partial sum rmax^2 + 2 a rmax);
+// subnormal operands / sums: absolute 2^-25 in scaled units.  The FP32 terms are those of the BF16 modes.
+constexpr float F16_R_MAX = 176.0f;
+__host__ __device__ inline float tensor_f16_ref_scale(float rmax_sampled)  // power of two, sampled radius -> [4, 8)
+{
+    if (!(rmax_sampled > 1e-30f) || !(rmax_sampled < 1e30f)) return 1.0f;
+    int e;
+    frexpf(rmax_sampled, &e);  // rmax = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.0f, 3 - e);
+}
+__host__ __device__ inline float tensor_f16_query_scale(float A, float R)  // 0 = unusable
+{
+    if (!(A <= 1e30f) || !(R <= F16_R_MAX)) return 0.0f;
+    float lim = 256.0f;
+    const float p = R * (R + 2.0f * A);
+    if (p > 0.0f) lim = fminf(lim, 32768.0f / p);
+    if (A > 0.0f) lim = fminf(lim, 16384.0f / A);
+    if (!(lim >= 6.1035156e-5f)) return 0.0f;
+    int e;
+    const float f = frexpf(lim, &e);  // lim = f * 2^e
+    (void)f;
+    return ldexpf(1.0f, e - 1);       // largest power of two <= lim
+}
+__host__ __device__ inline float tensor_error_bound_f16(int KP, int k, float a, float rmax, float s, float t)
+{
+    const float u24 = 5.9604645e-8f, u11 = 4.8828125e-4f;
+    const int steps = KP / 16;
+    const float big = rmax * rmax + 2.0f * a * rmax;
+    const float sub = (sqrtf((float)k) * (2.0f * t * s * a + s * rmax) + (float)(steps + 3)) * 2.9802322e-8f / (t * s * s);
+    const float E = (2.0f * u11 * 1.001f + (float)KP * 2.04f * 4.7683716e-7f) * a * rmax + (float)steps * u11 * 1.016f * 1.002f * big + sub +
+                    (KP + 5) * u24 * rmax * rmax + (KP + 8) * u24 * (a + rmax) * (a + rmax);
+    return E * 1.05f;
+}
 
 // ---------------------------------------------------------------------------------------------
 // candidates

@@ -79,6 +79,13 @@ __device__ __forceinline__ __nv_bfloat16 bf16_part(float x, int part)
     return __float2bfloat16_rn((fabsf(x) < inf_f()) ? rem : 0.0f);
 }
 
+// 16-bit operand element: BF16 (hi / lo part) or, in F16 mode, F16 of the scaled value
+__device__ __forceinline__ unsigned short operand_bits(float x, int part, bool f16, float scale)
+{
+    if (f16) return __half_as_ushort(__float2half_rn(x * scale));
+    return __bfloat16_as_ushort(bf16_part(x, part));
+}
+
 // ---------------------------------------------------------------------------------------------
 // reference-side preparation (part of index_build for k <= 128)
 // ---------------------------------------------------------------------------------------------
@@ -129,11 +136,13 @@ __global__ void tensor_centre_kernel(float* __restrict__ hdr, const int k, const
 
 // one CTA per 128-reference block: BF16 image of r' = fl(r - c) (TensorGeom layout) with |r'|^2
 // (FP32, split into three BF16 terms; +INF for padded lanes) in columns norm_col .. norm_col + 2.
+// F16 mode (f16 != 0): F16 image of s r' with s^2 |r'|^2, s = hdr[THDR_SCALE]; a reference outside the range the
+// scaling was chosen for (s |r'| > F16_R_MAX) flags the section unusable.
 // Like index_build_kernel it can store to the same slice of several peer GPUs' sections.
 __global__ void __launch_bounds__(128)
 tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int k, const TensorGeom g,
                         float* __restrict__ hdr, const int max_word, const int flag_word, const ImageDsts dst,
-                        const unsigned* __restrict__ mode_word, const unsigned my_mode)
+                        const unsigned* __restrict__ mode_word, const unsigned my_mode, const int f16)
 {
     if (tensor_mode_mismatch(mode_word, my_mode)) return;
     const long long b = blockIdx.x;
@@ -142,6 +151,7 @@ tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int
     const bool valid = j < n;
     const float* col = blocks + (size_t)b * (k + 1) * LB + row;  // coordinate t of this reference: col[t * LB]
     const size_t img_off = (size_t)b * image_bytes(T_BN, g.KB, g.KS);
+    const float s = f16 ? hdr[THDR_SCALE] : 1.0f;
     // |r'|^2 first (ascending dimensions), because its columns may share a chunk with data columns
     float rn = 0.0f;
     bool bad = false;
@@ -156,21 +166,34 @@ tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int
         rn = __fmaf_rn(x, x, rn);
     }
     const float rv = valid ? rn : inf_f();  // padded lanes can never be a tile minimum
-    const __nv_bfloat16 n_hi = __float2bfloat16_rn(rv);
-    const float rem1 = (rv < inf_f()) ? rv - __bfloat162float(n_hi) : 0.0f;
-    const __nv_bfloat16 n_mid = __float2bfloat16_rn(rem1);
-    const __nv_bfloat16 n_lo = __float2bfloat16_rn(rem1 - __bfloat162float(n_mid));
+    unsigned short n_hi, n_mid, n_lo;
+    bool wipe = false;  // F16: a finite reference out of range -> +INF score, no INF * 0 in the contraction
+    if (f16) {
+        const float nv = rv * s * s;  // power-of-two scaling: exact
+        if (valid && rn < inf_f() && !(nv <= F16_R_MAX * F16_R_MAX)) { bad = true; wipe = true; }
+        const __half h_hi = __float2half_rn(wipe ? inf_f() : nv);
+        const float rem1 = (__half2float(h_hi) < inf_f()) ? nv - __half2float(h_hi) : 0.0f;
+        const __half h_mid = __float2half_rn(rem1);
+        const __half h_lo = __float2half_rn(rem1 - __half2float(h_mid));
+        n_hi = __half_as_ushort(h_hi); n_mid = __half_as_ushort(h_mid); n_lo = __half_as_ushort(h_lo);
+    } else {
+        const __nv_bfloat16 b_hi = __float2bfloat16_rn(rv);
+        const float rem1 = (rv < inf_f()) ? rv - __bfloat162float(b_hi) : 0.0f;
+        const __nv_bfloat16 b_mid = __float2bfloat16_rn(rem1);
+        const __nv_bfloat16 b_lo = __float2bfloat16_rn(rem1 - __bfloat162float(b_mid));
+        n_hi = __bfloat16_as_ushort(b_hi); n_mid = __bfloat16_as_ushort(b_mid); n_lo = __bfloat16_as_ushort(b_lo);
+    }
     const int chunks = g.KB * 8 + g.KS * 2;
     for (int ch = 0; ch < chunks; ++ch) {
-        __align__(16) __nv_bfloat16 v[8];
+        __align__(16) unsigned short v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = ch * 8 + e;
             int dim, part;
             image_column(k, g.ndata, g.split != 0, c, false, dim, part);
             float x = 0.0f;
-            if (valid && dim >= 0) x = __fsub_rn(__ldg(col + (size_t)dim * LB), hdr[dim]);
-            __nv_bfloat16 o = bf16_part(x, part);
+            if (valid && !wipe && dim >= 0) x = __fsub_rn(__ldg(col + (size_t)dim * LB), hdr[dim]);
+            unsigned short o = operand_bits(x, part, f16 != 0, s);
             if (c == g.norm_col) o = n_hi;
             if (c == g.norm_col + 1) o = n_mid;
             if (c == g.norm_col + 2) o = n_lo;
@@ -189,12 +212,13 @@ tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int
 // query-side preparation (per search call)
 // ---------------------------------------------------------------------------------------------
 // one CTA per 256-query strip: BF16 image of -2 q' (TensorGeom layout, 1 in the norm columns),
-// band[q] = 2 E(q), approx_min[q] = +INF (ordered encoding)
+// band[q] = 2 E(q), approx_min[q] = +INF (ordered encoding).
+// F16 mode: F16 image of -2 t s q' with t in the norm columns, qscale[q] = t s^2 (0 = the query cannot be screened)
 __global__ void __launch_bounds__(256)
 tensor_query_image_kernel(const float* __restrict__ queries, const int m, const int k, const TensorGeom g,
                           const float* __restrict__ hdr, unsigned char* __restrict__ image,
-                          float* __restrict__ band, unsigned* __restrict__ approx_min,
-                          const unsigned* __restrict__ mode_word, const unsigned my_mode)
+                          float* __restrict__ band, unsigned* __restrict__ approx_min, float* __restrict__ qscale,
+                          const unsigned* __restrict__ mode_word, const unsigned my_mode, const int f16)
 {
     if (tensor_mode_mismatch(mode_word, my_mode)) return;
     const int row = threadIdx.x, rows = blockDim.x;  // rows per strip: 256, or 128 for the longest contractions
@@ -207,9 +231,14 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         const float x = valid ? __fsub_rn(__ldg(queries + q * k + t), hdr[t]) : 0.0f;
         qn = __fmaf_rn(x, x, qn);
     }
+    const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[THDR_MAX]);
+    const float a = sqrtf(qn), rmax = sqrtf(r2);
+    const float s = f16 ? hdr[THDR_SCALE] : 1.0f;
+    const float tq = f16 ? tensor_f16_query_scale(s * a, s * rmax) : 1.0f;  // 0: not representable
+    const float xs = f16 ? -2.0f * tq * s : -2.0f;                            // power of two: exact
     const int chunks = g.KB * 8 + g.KS * 2;
     for (int ch = 0; ch < chunks; ++ch) {
-        __align__(16) __nv_bfloat16 v[8];
+        __align__(16) unsigned short v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int col = ch * 8 + e;
@@ -217,25 +246,20 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
             image_column(k, g.ndata, g.split != 0, col, true, dim, part);
             float x = 0.0f;
             if (valid && dim >= 0) x = __fsub_rn(__ldg(queries + q * k + dim), hdr[dim]);
-            __nv_bfloat16 o = bf16_part(-2.0f * x, part);
-            if (col >= g.norm_col && col < g.norm_col + 3) o = __float2bfloat16_rn(1.0f);
+            unsigned short o = f16 ? __half_as_ushort(__float2half_rn(xs * x)) : __bfloat16_as_ushort(bf16_part(-2.0f * x, part));
+            if (col >= g.norm_col && col < g.norm_col + 3) o = f16 ? __half_as_ushort(__float2half_rn(tq)) : __bfloat16_as_ushort(__float2bfloat16_rn(1.0f));
             v[e] = o;
         }
         *reinterpret_cast<uint4*>(img + image_chunk_at(rows, g.KB, row, ch)) = *reinterpret_cast<const uint4*>(v);
     }
     if (valid) {
-        // E(q) >= |S~ - S| + |d_V0 - D'| for every reference (see the file header):
-        //   bf16 rounding of both operands   2^-7 (1 + 2^-9) |q'| |r'|
-        //   FP32 accumulation in the MMA     K 2^-23 * 2.02 |q'| |r'|
-        //   FP32 |r'|^2 and its 3-term split (K+1) 2^-24 |r'|^2 + 2^-22 |r'|^2
-        //   centring + V0 rounding           (K+8) 2^-24 (|q'| + |r'|)^2
-        const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[THDR_MAX]);
-        const float a = sqrtf(qn), rmax = sqrtf(r2);
-        const float E = tensor_error_bound(g.split != 0, KP, a, rmax);
-        const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[THDR_FLAGS] & 1u) != 0;  // NaN / INF / huge references
-        const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f);  // false for NaN too
+        // E(q) >= |S~ - S| + |d_V0 - D'| for every reference: tensor_error_bound / tensor_error_bound_f16 (tensor_common.cuh)
+        const float E = f16 ? tensor_error_bound_f16(KP, k, a, rmax, s, tq > 0.0f ? tq : 1.0f) : tensor_error_bound(g.split != 0, KP, a, rmax);
+        const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[THDR_FLAGS] & 1u) != 0;  // NaN / INF / huge / out-of-range references
+        const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f) && (tq > 0.0f);  // false for NaN too
         band[q] = usable ? 2.0f * E : inf_f();
         approx_min[q] = f2ord(inf_f());
+        if (qscale) qscale[q] = f16 ? (tq > 0.0f ? tq * s * s : 1.0f) : 1.0f;
     }
 }
 
@@ -262,12 +286,20 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
 // (tools/tensor_trace2.py: the epilogue warps start waiting before the unit is even issued).  With ISS = 2
 // (only for SUB = 2) issuer i issues sub-unit i of every tile into the buffers of team i; both wait for a B
 // stage and both commit its release.
-template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS, int ISS>
-__global__ void __maxnreg__(T_MAX_REGS)
+// F16 = F16 operands and F16 accumulators (THDR_MODE = TMODE_F16): the epilogue reads the accumulators two per
+// register (tcgen05.ld ... pack::16b) and reduces them with HMNMX2, which retires twice the values per clock of
+// FMNMX3; scores are in units of qscale[q] (a power of two) and are compared / recorded unscaled.
+// TEAMS = epilogue teams of 8 warps (F16 only; the FP32-accumulator epilogues are written for T_TEAMS): a team's units are
+// a serial chain per warp (wait, TMEM load ~140 clk, release, reduce, test: ~300 clk), so units complete at
+// ~300 / TEAMS clk; the 16-bit epilogue needs 60 registers, which leaves room for a third team (28 warps, 72 registers).
+constexpr int screen_max_regs(int iss, int teams) { return (16384 / (32 * ((1 + iss + teams * T_TEAM_WARPS + 3) / 4))) & ~7; }  // registers are per scheduler
+__host__ __device__ constexpr int screen_lcm(int a, int b) { int x = a; while (x % b) x += a; return x; }
+template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS, int ISS, bool F16, int TEAMS>
+__global__ void __maxnreg__(screen_max_regs(ISS, TEAMS))
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
-                     const float* __restrict__ band, unsigned* __restrict__ approx_min, const CandBuf cb,
-                     const unsigned* __restrict__ mode_word, const unsigned my_mode)
+                     const float* __restrict__ band, unsigned* __restrict__ approx_min, const float* __restrict__ qscale,
+                     const CandBuf cb, const unsigned* __restrict__ mode_word, const unsigned my_mode)
 {
     if (tensor_mode_mismatch(mode_word, my_mode)) return;  // the other precision variant of this launch pair runs
     // KB 64-column swizzled blocks (one 128-byte swizzle row each), then KS interleaved 16-column steps
@@ -282,10 +314,18 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     static_assert(TS || 2 * NBUF * SN <= 512, "accumulators exceed the 512 TMEM columns");
     constexpr uint32_t A_SMEM = TS ? 0u : A_BYTES;
     constexpr int SERVICE = 1 + ISS;           // warp 0 = TMA producer, warps 1 .. ISS = MMA issuers
-    static_assert(ISS == 1 || (ISS == 2 && SUB == 2 && NBUF == 4), "two issuers: sub-unit i of every tile, buffers i and i + 2");
+    static_assert(ISS == 1 || (ISS <= G * SUB && ((NBUF == 4 && (ISS == 2 || ISS == 4)) || (NBUF == 3 && ISS == 3 && F16))),
+                  "several issuers: issuer i takes the units u % ISS == i and must own whole buffers");
+    // Accumulator barriers.  A barrier may only ever be waited on by ONE team, in phase order (a waiter one phase ahead
+    // misreads its parity).  With 2 or 4 buffers a buffer belongs to one team; with 3 buffers the two teams alternate on
+    // a buffer, which is only safe while one thread issues all units in order -- several issuers complete their units
+    // in any order, so then there is one barrier pair per (buffer, team): unit u uses barrier u % NB, NB = lcm(NBUF, 2).
+    constexpr int SPIN = F16 ? NNS_T_SPIN_F16 : NNS_T_SPIN;
+    constexpr int NB = ISS > 1 ? screen_lcm(NBUF, TEAMS) : NBUF;
+    static_assert(F16 || TEAMS == T_TEAMS, "only the 16-bit epilogue takes a team count");
     constexpr int CPU = SN / 32;               // 32-column chunks per unit
-    // instruction descriptor: D = F32, A = B = BF16, both K-major, N = SN, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // instruction descriptor: D = F32, A = B = BF16 (F16 mode: D = A = B = F16, format code 0), both K-major, N = SN, M = 128
+    constexpr uint32_t IDESC = (F16 ? 0u : ((1u << 4) | (1u << 7) | (1u << 10))) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_smem = smem;
     unsigned char* b_smem = smem + A_SMEM;
@@ -294,7 +334,8 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
     unsigned* s_cand_count = tmem_slot + 1;
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_full = bar0, b_empty = bar0 + 8 * T_STAGES;
-    const uint32_t acc_full = bar0 + 8 * 2 * T_STAGES, acc_empty = acc_full + 8 * NBUF, a_full = acc_empty + 8 * NBUF;
+    const uint32_t acc_full = bar0 + 8 * 2 * T_STAGES, acc_empty = acc_full + 8 * NB, a_full = acc_empty + 8 * NB;
+    static_assert(2 * T_STAGES + 2 * NB + 1 <= 2 * T_MAX_STAGES + 8, "mbarrier area");
 
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     const int t0 = (int)blockIdx.y * tiles_per_split;
@@ -314,7 +355,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < T_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, ISS); }
-        for (int i = 0; i < NBUF; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_TEAM_WARPS); }
+        for (int i = 0; i < NB; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, T_TEAM_WARPS); }
         mbar_init(a_full, TS ? T_TEAM_WARPS : 1);
         mbar_fence_init();
         *s_cand_count = 0;
@@ -384,8 +425,10 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             // one accumulator unit: references [sub * SN, sub * SN + SN) of the current tile into buffer `buf`
             // tile_first / tile_last: this is the issuing thread's first / last unit of the tile
             auto issue_unit = [&](const int u, const int buf, const int sub, const bool tile_first, const bool tile_last) {
-                mbar_wait_mma(acc_empty + 8 * buf, (uint32_t)(((u / NBUF) & 1) ^ 1));  // its team drained this buffer
-                if (j == 0 && tile_first) mbar_wait_mma(b_full + 8 * s, ph);             // TMA landed this stage
+                T_TRACE(1, u);
+                mbar_wait_mma<SPIN>(acc_empty + 8 * buf, (uint32_t)(((u / NBUF) & 1) ^ 1));  // its team drained this buffer
+                if (j == 0 && tile_first) mbar_wait_mma<SPIN>(b_full + 8 * s, ph);             // TMA landed this stage
+                T_TRACE(2, u);
                 tc_fence_after();
                 // rows sub * SN .. of the B tile: SN rows of 128 B in a swizzled block, of 16 B in an interleaved chunk
                 const uint32_t sw16 = boff16 + (uint32_t)(sub * SN * 128 >> 4), il16 = boff16 + (uint32_t)(sub * SN * 16 >> 4);
@@ -436,12 +479,65 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                         }
                 }
             } else {
-                // issuer `id` = sub-unit `id` of every tile: units 2 t + id, buffers id and id + 2 alternately
+                // issuer `id` takes the units u % ISS == id (sub-unit id % 2 of every (ISS / 2)-th tile; with four issuers
+                // each owns ONE accumulator buffer).  The issuing thread's own instruction stream is slow (one active
+                // thread, dependent scalar code: tools/tensor_trace2.py shows ~370 clk between its commit and its next
+                // wait), so what keeps the tensor pipe fed is the number of threads that issue, not their speed.
                 const int id = warp - 1;
-                for (int t = 0; t < nt; t += 2) {
-                    issue_unit(2 * t + id, id, id, true, true);
-                    if (t + 1 < nt) issue_unit(2 * (t + 1) + id, id + 2, id, true, true);
+                const int nunits = nt * SUB;
+                constexpr int UPGRP = G * SUB;         // units per B stage (G tiles): every issuer has at least one of them
+                int sg = 0, held = -1;                 // stage / tile group this thread currently reads
+                uint32_t phg = 0;
+                int nb = id % NB;                      // u % NB
+                uint32_t par = 0;                      // (u / NB) & 1
+                for (int u = id; u < nunits; u += ISS) {
+                    const int grp = u / UPGRP;
+                    if (grp != held) {
+                        if (held >= 0) {               // done with the previous stage once this thread's MMAs have read it
+                            tc_commit(b_empty + 8 * sg);
+                            if (++sg == T_STAGES) { sg = 0; phg ^= 1u; }
+                        }
+                        mbar_wait_mma<SPIN>(b_full + 8 * sg, phg);   // TMA landed this stage
+                        held = grp;
+                    }
+                    static_assert(NB == NBUF || NB == 2 * NBUF, "barrier <-> buffer mapping");
+                    const int buf = (NB == NBUF) ? nb : (nb >= NBUF ? nb - NBUF : nb);
+                    // the previous user of this buffer, unit u - NBUF, has been drained (fresh barrier: parity 1 passes)
+                    const int eb = (NB == NBUF) ? nb : (nb >= NBUF ? nb - NBUF : nb + NBUF);
+                    const uint32_t epar = (NB == NBUF) ? (par ^ 1u) : (nb >= NBUF ? par : (par ^ 1u));
+                    T_TRACE(1, u);
+                    mbar_wait_mma<SPIN>(acc_empty + 8 * eb, epar);
+                    T_TRACE(2, u);
+                    tc_fence_after();
+                    const int uin = u - grp * UPGRP;   // unit within the group
+                    const uint32_t b16 = (uint32_t)sg * (STAGE_BYTES >> 4) + (uint32_t)(uin / SUB) * (B_BYTES >> 4);
+                    const uint32_t sw16 = b16 + (uint32_t)((uin % SUB) * SN * 128 >> 4), il16 = b16 + (uint32_t)((uin % SUB) * SN * 16 >> 4);
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const u64 bdesc = ((u64)bdesc_sw_hi << 32) | (u64)(bdesc_sw_lo[kb][ks] + sw16);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                if (TS) tc_mma_bf16_ts(tmem_base + (uint32_t)((buf * 2 + h) * SN), tmem_base + A_COL0 + (uint32_t)((h * STEPS + kb * 4 + ks) * 8), bdesc, IDESC, (uint32_t)((kb | ks) != 0));
+                                else tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_sw[kb][ks][h], bdesc, IDESC, (uint32_t)((kb | ks) != 0));
+                            }
+                        }
+#pragma unroll
+                    for (int xs = 0; xs < KS; ++xs) {
+                        const u64 bdesc = ((u64)bdesc_il_hi << 32) | (u64)(bdesc_il_lo[xs] + il16);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (TS) tc_mma_bf16_ts(tmem_base + (uint32_t)((buf * 2 + h) * SN), tmem_base + A_COL0 + (uint32_t)((h * STEPS + KB * 4 + xs) * 8), bdesc, IDESC, (uint32_t)((KB | xs) != 0));
+                            else tc_mma_bf16(tmem_base + (uint32_t)((buf * 2 + h) * SN), adesc_il[xs][h], bdesc, IDESC, (uint32_t)((KB | xs) != 0));
+                        }
+                    }
+                    tc_commit(acc_full + 8 * nb);   // accumulator complete
+                    T_TRACE(3, u);
+                    nb += ISS;
+                    if (nb >= NB) { nb -= NB; par ^= 1u; }
                 }
+                if (held >= 0) tc_commit(b_empty + 8 * sg);
             }
         }
     } else {
@@ -531,7 +627,85 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
         // a load is in flight under every 32-value reduction; the loop body covers two units, and the four chunk
         // minima are tested against the threshold ONCE (a threshold that is one unit stale only admits more
         // candidates), so a trip has two taken branches instead of six.
-        if constexpr (NNS_T_PIPE == 1 && CPU == 2 && NNS_T_EXPERIMENT == 0) {
+        if constexpr (F16) {
+            // ---- 16-bit accumulators: 64 columns per load (32 registers), two loads (128 columns) per loop trip and ONE
+            // candidate test per trip; 15 HMNMX2 reduce a 32-reference chunk to one register holding two partial minima ----
+            static_assert(SN % 64 == 0, "F16 epilogue reads 64 columns at a time");
+            constexpr int GPU_ = SN / 64;            // 64-column groups per accumulator unit
+            constexpr int UPT = GPU_ == 1 ? 2 : 1;   // units per trip
+            uint32_t w[32];
+            const int nunits = nt * SUB;
+            const float uq = (q < m) ? __ldg(qscale + q) : 1.0f, inv_uq = 1.0f / uq;  // powers of two
+            float thresh_s = thresh * uq;            // the threshold in accumulator units
+            auto hmin16 = [&](const int o) -> uint32_t {
+                uint32_t c0 = hmin2(w[o + 0], w[o + 1]), c1 = hmin2(w[o + 2], w[o + 3]), c2 = hmin2(w[o + 4], w[o + 5]), c3 = hmin2(w[o + 6], w[o + 7]);
+                c0 = hmin2(c0, w[o + 8]); c1 = hmin2(c1, w[o + 9]); c2 = hmin2(c2, w[o + 10]); c3 = hmin2(c3, w[o + 11]);
+                c0 = hmin2(c0, w[o + 12]); c1 = hmin2(c1, w[o + 13]); c2 = hmin2(c2, w[o + 14]); c3 = hmin2(c3, w[o + 15]);
+                return hmin2(hmin2(c0, c1), hmin2(c2, c3));
+            };
+            auto emit_h = [&](const uint32_t mh, const int unit32) {  // rare path
+                const float cm = hmin2_to_float(mh) * inv_uq;
+                if (cm <= thresh) {
+                    TensorCand cnd;
+                    cnd.q = (int)q; cnd.unit = unit32; cnd.smin = cm;
+                    cand_emit(cb, s_cand_count, cta, cnd);
+                    if (cm < run_min && !cb.fixed_threshold) {
+                        run_min = cm;
+                        thresh = run_min + my_band;
+                        thresh_s = thresh * uq;
+                        atomicMin(approx_min + q, f2ord(run_min));
+                    }
+                }
+            };
+            int nb = team;                           // u % NB of the next unit of this team (team < TEAMS <= NB)
+            uint32_t par = 0;                        // (u / NB) & 1
+#pragma unroll 1
+            for (int u = team; u < nunits; u += UPT * TEAMS) {
+                uint32_t mm[4];
+#pragma unroll
+                for (int j = 0; j < UPT; ++j) {
+                    const int uj = u + j * TEAMS;
+                    if (j > 0 && uj >= nunits) {
+#pragma unroll
+                        for (int gq = 0; gq < 2 * GPU_; ++gq) mm[2 * GPU_ * j + gq] = 0x7c007c00u;  // +INF, +INF
+                        continue;
+                    }
+                    const int bar = nb;
+                    const uint32_t bpar = par;
+                    const int buf = (NB == NBUF) ? nb : (nb >= NBUF ? nb - NBUF : nb);
+                    nb += TEAMS;
+                    if (nb >= NB) { nb -= NB; par ^= 1u; }
+                    if (lane == 0) T_TRACE(24 + (e & 7), uj);   // [24..31] started waiting (trace rows are per warp of the unit's team)
+                    mbar_wait_hot<SPIN>(acc_full + 8 * bar, bpar);
+                    if (lane == 0) T_TRACE(4 + (e & 7), uj);    // [4..11] accumulator ready
+                    tc_fence_after();
+#pragma unroll
+                    for (int gq = 0; gq < GPU_; ++gq) {
+                        tmem_ld64_pack16(lane_base + (uint32_t)(buf * 2 * SN + gq * 64), w);
+                        tmem_ld_wait();
+                        if (gq == GPU_ - 1) {  // every TMEM read of this warp for the unit has completed
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty + 8 * bar);
+                            if (lane == 0) T_TRACE(12 + (e & 7), uj);   // [12..19] released
+                        }
+                        mm[2 * (GPU_ * j + gq)] = hmin16(0);
+                        mm[2 * (GPU_ * j + gq) + 1] = hmin16(16);
+                    }
+                }
+                const float all = hmin2_to_float(hmin2(hmin2(mm[0], mm[1]), hmin2(mm[2], mm[3])));
+                if (all <= thresh_s) {
+#pragma unroll
+                    for (int j = 0; j < UPT; ++j) {
+                        const int uj = u + j * TEAMS;
+                        if (j > 0 && uj >= nunits) continue;
+                        const int unit0 = t0 * (T_BN / 32) + uj * CPU;
+#pragma unroll
+                        for (int c = 0; c < 2 * GPU_; ++c) emit_h(mm[2 * GPU_ * j + c], unit0 + c);
+                    }
+                }
+            }
+        } else if constexpr (NNS_T_PIPE == 1 && CPU == 2 && NNS_T_EXPERIMENT == 0) {
             uint32_t va[32], vb[32];
             const int nunits = nt * SUB;
             auto min32 = [&](const uint32_t (&cur)[32]) -> float {
@@ -563,7 +737,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 }
             };
             auto acquire = [&](const int u) {  // unit u's accumulator is complete
-                mbar_wait_hot(acc_full + 8 * (u % NBUF), (uint32_t)((u / NBUF) & 1));
+                mbar_wait_hot<SPIN>(acc_full + 8 * (u % NBUF), (uint32_t)((u / NBUF) & 1));
                 tc_fence_after();
             };
             auto release = [&](const int u) {  // every TMEM read of this warp for unit u has completed
@@ -649,7 +823,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
                 }
             };
             auto acquire3 = [&](const int u) {
-                mbar_wait_hot(acc_full + 8 * (u % NBUF), (uint32_t)((u / NBUF) & 1));
+                mbar_wait_hot<SPIN>(acc_full + 8 * (u % NBUF), (uint32_t)((u / NBUF) & 1));
                 tc_fence_after();
             };
             auto release3 = [&](const int u) {
@@ -715,7 +889,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             auto unit = [&](const int u, float& m0, float& m1) {
                 const int buf = u % NBUF;
                 if (lane == 0) T_TRACE(24 + (e & 7), u);   // [24..31] started waiting (trace rows are per warp of the unit's team)
-                mbar_wait_hot(acc_full + 8 * buf, (uint32_t)((u / NBUF) & 1));
+                mbar_wait_hot<SPIN>(acc_full + 8 * buf, (uint32_t)((u / NBUF) & 1));
                 if (lane == 0) T_TRACE(4 + (e & 7), u);    // [4..11] accumulator ready
                 tc_fence_after();
                 tmem_ld64(lane_base + (uint32_t)(buf * 2 * SN), w);
@@ -755,7 +929,7 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             const int buf = u % NBUF;
             const uint32_t taddr = lane_base + (uint32_t)(buf * 2 * SN);
             const int unit0 = t0 * (T_BN / 32) + u * CPU;
-            mbar_wait_hot(acc_full + 8 * buf, (uint32_t)((u / NBUF) & 1));
+            mbar_wait_hot<SPIN>(acc_full + 8 * buf, (uint32_t)((u / NBUF) & 1));
             if (lane == 0) T_TRACE(4 + e, u);
             tc_fence_after();
             if constexpr (LD64) {
@@ -926,13 +1100,15 @@ cudaError_t tensor_image_build(int k, int cn, const float* d_blocks_part, float*
     const int nb = write_blocks > 0 ? write_blocks : (cn + LB - 1) / LB;
     if (nb <= 0 || k < 1 || k > TENSOR_MAX_K) return cudaSuccess;
     const TensorGeom g = tensor_geom(k);  // slices of a shared index: always the default (split) layout
-    tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks_part, cn, k, g, d_hdr, max_word, flag_word, dst, nullptr, 0u);
+    tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks_part, cn, k, g, d_hdr, max_word, flag_word, dst, nullptr, 0u, 0);
     return cudaGetLastError();
 }
 
-// ---- precision-mode probe (TENSOR_PLAIN_MIN_K <= k <= TENSOR_SPLIT_MAX_K) ----
+// ---- precision mode (TENSOR_PLAIN_MIN_K <= k <= 128) ----
+// k <= TENSOR_SPLIT_MAX_K: split-precision BF16 or plain F16, decided per index by a probe; above: plain F16 (a section
+// built in slices by several GPUs / processes keeps the default BF16 layout: its scale would have to be agreed first)
 constexpr int TENSOR_PROBE_SAMPLES = 128;
-bool tensor_has_modes(int k) { return k >= TENSOR_PLAIN_MIN_K && k <= TENSOR_SPLIT_MAX_K; }
+bool tensor_has_modes(int k) { return k >= TENSOR_PLAIN_MIN_K && k <= 128; }
 
 // sample s = reference number s * stride, copied out of the tiled-SoA blocks as an AoS query
 __global__ void tensor_probe_gather_kernel(const float* __restrict__ blocks, const int n, const int k, const long long stride,
@@ -964,32 +1140,37 @@ tensor_rmax_sample_kernel(const float* __restrict__ blocks, const int n, const i
     if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + THDR_MAX + 4, bits);
 }
 
-// One warp.  For every sample: d1 = distance to its nearest OTHER reference (second entry of its 2-NN list;
-// 0 for duplicated points), E = the plain-BF16 error bound at that point; (1 + 2E/d1)^(k/2) estimates how
-// many references fall inside the plain band (locally uniform density in k dimensions -- an over-estimate
-// for data of lower intrinsic dimension, which errs towards split precision).  Plain mode is chosen when
-// that estimate is <= 32 for three quarters of the samples.
-__global__ void tensor_mode_kernel(float* __restrict__ hdr, const float* __restrict__ index_header, const float* __restrict__ samples,
-                                   const u64* __restrict__ keys2, const int count, const int k, const int KP_plain)
+// One warp.  Fixes the F16 reference scale from the sampled radius and chooses the mode.  With a probe, for every
+// sample: d1 = distance to its nearest OTHER reference (second entry of its 2-NN list; 0 for duplicated points),
+// E = the F16 error bound at that point; (1 + 2E/d1)^(k/2) estimates how many references fall inside the plain band
+// (locally uniform density in k dimensions -- an over-estimate for data of lower intrinsic dimension, which errs
+// towards split precision).  F16 is chosen when that estimate is <= 32 for three quarters of the samples.
+__global__ void tensor_mode_kernel(float* __restrict__ hdr, const float* __restrict__ samples, const u64* __restrict__ keys2,
+                                   const int count, const int k, const int KP_plain, const int probe)
 {
     const int lane = (int)threadIdx.x;
-    (void)index_header;
     const float rmax = sqrtf(__uint_as_float(reinterpret_cast<const unsigned*>(hdr)[THDR_MAX + 4]));  // sampled max |r'|
+    const float s = tensor_f16_ref_scale(rmax);
     int ok = 0;
-    for (int s = lane; s < count; s += 32) {
+    for (int smp = lane; probe && smp < count; smp += 32) {
         float qn = 0.0f;
         for (int t = 0; t < k; ++t) {
-            const float x = samples[(size_t)s * k + t] - hdr[t];
+            const float x = samples[(size_t)smp * k + t] - hdr[t];
             qn = __fmaf_rn(x, x, qn);
         }
-        const float E = tensor_error_bound(false, KP_plain, sqrtf(qn), rmax);
-        const float d1 = __uint_as_float((unsigned)(keys2[(size_t)s * 2 + 1] >> 32));
+        const float a = sqrtf(qn);
+        const float tq = tensor_f16_query_scale(s * a, s * rmax);
+        const float E = tq > 0.0f ? tensor_error_bound_f16(KP_plain, k, a, rmax, s, tq) : inf_f();
+        const float d1 = __uint_as_float((unsigned)(keys2[(size_t)smp * 2 + 1] >> 32));
         const float est = (d1 > 0.0f && d1 < inf_f()) ? expf(0.5f * (float)k * log1pf(2.0f * E / d1)) : inf_f();
         ok += (est <= 32.0f) ? 1 : 0;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, off);
-    if (lane == 0) reinterpret_cast<unsigned*>(hdr)[THDR_MODE] = (rmax <= 1e15f && 4 * ok >= 3 * count) ? 1u : 0u;
+    if (lane == 0) {
+        hdr[THDR_SCALE] = s;
+        reinterpret_cast<unsigned*>(hdr)[THDR_MODE] = (rmax <= 1e15f && (!probe || 4 * ok >= 3 * count)) ? TMODE_F16 : TMODE_DEFAULT;
+    }
 }
 
 cudaError_t tensor_index_build(int k, int n, const float* d_header, const float* d_blocks, float* d_section, cudaStream_t st)
@@ -1002,37 +1183,42 @@ cudaError_t tensor_index_build(int k, int n, const float* d_header, const float*
     dst.count = 1;
     const int nb = (n + LB - 1) / LB;
     const unsigned* mode_word = reinterpret_cast<const unsigned*>(d_section) + THDR_MODE;
-    const bool modes = tensor_has_modes(k) && n >= 4 * TENSOR_PROBE_SAMPLES && d_header != nullptr;
+    const bool probe = k <= TENSOR_SPLIT_MAX_K;  // below, split precision is the alternative and the data decides
+    const bool modes = tensor_has_modes(k) && (!probe || (n >= 4 * TENSOR_PROBE_SAMPLES && d_header != nullptr));
+    const TensorGeom gf = tensor_geom(k, true);
     if (modes) {
-        // probe: the 2 nearest references of TENSOR_PROBE_SAMPLES sample points (the exact FP32 top-K kernel)
-        const int S = TENSOR_PROBE_SAMPLES;
-        const int splits = topk_choose_splits(S, n, 148);
-        const size_t off_keys = ((size_t)S * k * sizeof(float) + 255) & ~(size_t)255;
-        const size_t off_scr = off_keys + (((size_t)S * 2 * sizeof(u64) + 255) & ~(size_t)255);
-        unsigned char* tmp = nullptr;
-        e = cudaMallocAsync((void**)&tmp, off_scr + topk_scratch_bytes(S, 2, splits), st);
-        if (e != cudaSuccess) return e;
-        float* samples = reinterpret_cast<float*>(tmp);
-        u64* keys2 = reinterpret_cast<u64*>(tmp + off_keys);
         const int stride = (nb + TENSOR_CENTRE_BLOCKS - 1) / TENSOR_CENTRE_BLOCKS;
         tensor_rmax_sample_kernel<<<(nb + stride - 1) / stride, 128, 0, st>>>(d_blocks, n, k, stride, d_section);
-        tensor_probe_gather_kernel<<<S, 32, 0, st>>>(d_blocks, n, k, (long long)n / S, samples);
-        e = launch_keys_init(keys2, 2 * S, st);
-        if (e == cudaSuccess) e = topk_search_launch(k, S, n, 2, samples, d_blocks, 0, keys2, reinterpret_cast<u64*>(tmp + off_scr), splits, false, st, nullptr);
-        if (e == cudaSuccess) {
-            const TensorGeom gp = tensor_geom(k, true);
-            tensor_mode_kernel<<<1, 32, 0, st>>>(d_section, d_header, samples, keys2, S, k, gp.KB * 64 + gp.KS * 16);
-            e = cudaGetLastError();
+        if (probe) {
+            // the 2 nearest references of TENSOR_PROBE_SAMPLES sample points (the exact FP32 top-K kernel)
+            const int S = TENSOR_PROBE_SAMPLES;
+            const int splits = topk_choose_splits(S, n, 148);
+            const size_t off_keys = ((size_t)S * k * sizeof(float) + 255) & ~(size_t)255;
+            const size_t off_scr = off_keys + (((size_t)S * 2 * sizeof(u64) + 255) & ~(size_t)255);
+            unsigned char* tmp = nullptr;
+            e = cudaMallocAsync((void**)&tmp, off_scr + topk_scratch_bytes(S, 2, splits), st);
+            if (e != cudaSuccess) return e;
+            float* samples = reinterpret_cast<float*>(tmp);
+            u64* keys2 = reinterpret_cast<u64*>(tmp + off_keys);
+            tensor_probe_gather_kernel<<<S, 32, 0, st>>>(d_blocks, n, k, (long long)n / S, samples);
+            e = launch_keys_init(keys2, 2 * S, st);
+            if (e == cudaSuccess) e = topk_search_launch(k, S, n, 2, samples, d_blocks, 0, keys2, reinterpret_cast<u64*>(tmp + off_scr), splits, false, st, nullptr);
+            if (e == cudaSuccess) {
+                tensor_mode_kernel<<<1, 32, 0, st>>>(d_section, samples, keys2, S, k, gf.KB * 64 + gf.KS * 16, 1);
+                e = cudaGetLastError();
+            }
+            const cudaError_t fe = cudaFreeAsync(tmp, st);
+            if (e != cudaSuccess) return e;
+            if (fe != cudaSuccess) return fe;
+        } else {
+            tensor_mode_kernel<<<1, 32, 0, st>>>(d_section, nullptr, nullptr, 0, k, gf.KB * 64 + gf.KS * 16, 0);
         }
-        const cudaError_t fe = cudaFreeAsync(tmp, st);
-        if (e != cudaSuccess) return e;
-        if (fe != cudaSuccess) return fe;
     }
     // the image in the layout of the chosen mode (both launches; the one that does not match exits at once)
     tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks, n, k, tensor_geom(k, false), d_section, THDR_MAX, THDR_FLAGS, dst,
-                                                modes ? mode_word : nullptr, 0u);
+                                                modes ? mode_word : nullptr, TMODE_DEFAULT, 0);
     if (modes)
-        tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks, n, k, tensor_geom(k, true), d_section, THDR_MAX, THDR_FLAGS, dst, mode_word, 1u);
+        tensor_ref_image_kernel<<<nb, 128, 0, st>>>(d_blocks, n, k, gf, d_section, THDR_MAX, THDR_FLAGS, dst, mode_word, TMODE_F16, 1);
     return cudaGetLastError();
 }
 
@@ -1054,31 +1240,44 @@ static size_t tensor_smem_bytes(const TensorGeom& g)
            (2 * T_MAX_STAGES + 8) * 8 + 16;
 }
 
-template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS, int ISS = 1>
+template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS, int ISS, bool F16, int TEAMS = T_TEAMS>
 static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
                                         const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
-                                        const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
+                                        const float* qscale, const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
 {
-    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS, F16, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS><<<grid, 32 * (1 + ISS + T_TEAMS * T_TEAM_WARPS), smem, st>>>(
-        qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode);
+    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS, F16, TEAMS><<<grid, 32 * (1 + ISS + TEAMS * T_TEAM_WARPS), smem, st>>>(
+        qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode);
     return cudaGetLastError();
 }
 
 // the screen kernel instantiated for operand geometry g: short contractions (k <= 9, or plain mid-k): SS form,
 // 4 buffers of 64 references; longer ones: A in TMEM (NNS_T_TS), 64-reference units in 3 buffers (2 where A
-// needs more than 128 columns)
-static cudaError_t tensor_screen_dispatch(const TensorGeom& g, dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage,
-                                          int m, const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
-                                          const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
+// needs more than 128 columns).  F16: the same shapes with 16-bit operands and accumulators.
+template <bool F16>
+static cudaError_t tensor_screen_dispatch_t(const TensorGeom& g, dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage,
+                                            int m, const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
+                                            const float* qscale, const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
 {
 #define NNS_SCREEN(KB_, KS_, ST_, G_, SUB_, NBUF_, TS_) \
-    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode)
+    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_, 1, F16>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode)
 #define NNS_SCREEN_ISS(KB_, KS_, ST_, G_, SUB_, NBUF_, TS_, ISS_) \
-    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_, ISS_>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, cb, mode_word, my_mode)
-    if (g.KB == 0 && g.KS == 1) return NNS_SCREEN_ISS(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false, (NNS_T_SUB == 2 ? NNS_T_ISS : 1));
-    if (g.KB == 0) return NNS_SCREEN_ISS(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false, (NNS_T_SUB == 2 ? NNS_T_ISS : 1));
+    tensor_screen_launch<KB_, KS_, ST_, G_, SUB_, NBUF_, TS_, ISS_, F16>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode)
+    // issuing threads: the FP32-accumulator epilogue needs 87 registers (one 64-column load), which allows 19 warps = 2 issuers;
+    // the 16-bit one needs 60, which allows 21 warps = one issuer per accumulator buffer
+    constexpr int ISS_ = NNS_T_SUB == 2 ? (F16 ? NNS_T_ISS_F16 : NNS_T_ISS) : 1;
+    if constexpr (F16 && NNS_T_SUB == 2 && NNS_T_ISS_F16 == 3) {
+        // A in TMEM, three buffers, one issuer per buffer: in the SS form an N = 64 MMA fetches 4 KiB of A and 2 KiB of B
+        // from shared memory, 48 clk at 128 B/clk for 32 clk of tensor work (measured: 58 clk per MMA on C3)
+        if (g.KB == 0 && g.KS == 1)
+            return tensor_screen_launch<0, 1, 6, 4, 2, 3, true, 3, F16, NNS_T_TEAMS_F16>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode);
+        if (g.KB == 0)
+            return tensor_screen_launch<0, 2, 6, 2, 2, 3, true, 3, F16, NNS_T_TEAMS_F16>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode);
+    } else {
+        if (g.KB == 0 && g.KS == 1) return NNS_SCREEN_ISS(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false, ISS_);
+        if (g.KB == 0) return NNS_SCREEN_ISS(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false, ISS_);
+    }
 #if NNS_T_TS == 1
     // measured on B200 (profiles/r2_tune_ts.txt): A in TMEM + three 64-reference buffers is 3 % faster at 64
     // columns (C3 split: 434 vs 446 ms) and 3 % slower at 144 (C4: 229 vs 223 ms), where the tensor pipe is busy
@@ -1102,11 +1301,55 @@ static cudaError_t tensor_screen_dispatch(const TensorGeom& g, dim3 grid, size_t
 #undef NNS_SCREEN_ISS
 }
 
+// One query batch through the screen: query image(s) + screen kernel(s).  For TENSOR_PLAIN_MIN_K <= k <= 128 the
+// index may hold either the default BF16 images or the F16 ones (THDR_MODE): both variants of every kernel are
+// launched and the one that does not match the header word exits at once -- no host round trip.
+struct ScreenSetup {
+    TensorGeom g, gf;          // default layout (sizes the scratch) / F16 plain layout
+    bool modes, longk;
+    const unsigned* mode_word;
+    int rows;
+    size_t smem, smem_f16;
+};
+static ScreenSetup screen_setup(int k, const float* d_section)
+{
+    ScreenSetup s{};
+    s.g = tensor_geom(k);
+    s.gf = tensor_geom(k, true);
+    s.modes = tensor_has_modes(k);
+    s.mode_word = s.modes ? reinterpret_cast<const unsigned*>(d_section) + THDR_MODE : nullptr;
+    s.longk = s.g.KB > 2;
+    s.rows = s.longk ? tensor_longk_rows(s.g.KB) : T_BM;
+    // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
+    // CTA is resident per SM even at KP = 64
+    s.smem = std::max(tensor_smem_bytes(s.g), (size_t)120 * 1024);
+    s.smem_f16 = std::max(tensor_smem_bytes(s.gf), (size_t)120 * 1024);
+    return s;
+}
+static cudaError_t screen_batch(const ScreenSetup& s, int k, const float* bq, int bm, int bs, int splits, const float* hdr,
+                                unsigned char* qimage, float* band, unsigned* amin, float* qscale, const unsigned char* rimage,
+                                int nblocks, int tps, const CandBuf& cb, cudaStream_t st, bool images_only = false, bool screen_only = false)
+{
+    cudaError_t e = cudaSuccess;
+    if (!screen_only) {
+        tensor_query_image_kernel<<<bs, s.rows, 0, st>>>(bq, bm, k, s.g, hdr, qimage, band, amin, qscale, s.mode_word, TMODE_DEFAULT, 0);
+        if (s.modes) tensor_query_image_kernel<<<bs, s.rows, 0, st>>>(bq, bm, k, s.gf, hdr, qimage, band, amin, qscale, s.mode_word, TMODE_F16, 1);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess || images_only) return e;
+    dim3 grid((unsigned)bs, (unsigned)splits);
+    if (s.longk) return tensor_longk_launch(s.g.KB, grid, st, qimage, bm, rimage, nblocks, tps, band, amin, cb);
+    e = tensor_screen_dispatch_t<false>(s.g, grid, s.smem, st, qimage, bm, rimage, nblocks, tps, band, amin, qscale, cb, s.mode_word, TMODE_DEFAULT);
+    if (e == cudaSuccess && s.modes)
+        e = tensor_screen_dispatch_t<true>(s.gf, grid, s.smem_f16, st, qimage, bm, rimage, nblocks, tps, band, amin, qscale, cb, s.mode_word, TMODE_F16);
+    return e;
+}
+
 __global__ void tensor_status_init_kernel(unsigned* __restrict__ status, const unsigned cap, unsigned* __restrict__ common, const int nbatches,
                                           const unsigned* __restrict__ mode_word, const unsigned kp_split, const unsigned kp_plain)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { status[0] = 0u; status[1] = 0u; status[2] = cap; status[3] = (mode_word && *mode_word) ? kp_plain : kp_split; }
+    if (i == 0) { status[0] = 0u; status[1] = 0u; status[2] = cap; status[3] = (mode_word && *mode_word) ? (kp_plain | (*mode_word << 16)) : kp_split; }
     if (i < nbatches) common[i] = 0u;
 }
 
@@ -1135,13 +1378,13 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
                           int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
                           int* launches, unsigned* d_stats, bool tiny_candidate_buffer)
 {
-    const TensorGeom g = tensor_geom(k);            // default layout (split where it exists): sizes the scratch
-    const TensorGeom gp = tensor_geom(k, true);     // plain layout, used when the index header says so
-    const bool modes = tensor_has_modes(k);
-    const unsigned* mode_word = modes ? reinterpret_cast<const unsigned*>(d_section) + THDR_MODE : nullptr;
+    const ScreenSetup ss = screen_setup(k, d_section);
+    const TensorGeom g = ss.g;                      // default layout (split where it exists): sizes the scratch
+    const TensorGeom gp = ss.gf;                    // F16 plain layout, used when the index header says so
+    const bool modes = ss.modes;
+    const unsigned* mode_word = ss.mode_word;
     const int nblocks = (n + LB - 1) / LB;
-    const bool longk = g.KB > 2;                                   // K-loop kernel (tensor_longk.cu)
-    const int rows = longk ? tensor_longk_rows(g.KB) : T_BM;       // query rows per strip / CTA
+    const int rows = ss.rows;                       // query rows per strip / CTA (the K-loop kernel of tensor_longk.cu: 256 or 128)
     const int strips = (m + rows - 1) / rows;
     const float* hdr = d_section;
     const unsigned char* rimage = reinterpret_cast<const unsigned char*>(d_section + TENSOR_HDR_FLOATS);
@@ -1210,7 +1453,8 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     const size_t qimg_bytes = (size_t)batch_strips * image_bytes(rows, g.KB, g.KS);
     const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
     const size_t off_amin = off_band + ((batch_queries * 4 + 255) & ~(size_t)255);
-    const size_t off_cnt = off_amin + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_qs = off_amin + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_cnt = off_qs + ((batch_queries * 4 + 255) & ~(size_t)255);
     const size_t off_ccnt = off_cnt + (((size_t)nbatches * 4 + 255) & ~(size_t)255);
     const size_t off_cand = off_ccnt + (((size_t)cb.n_ctas * 4 + 255) & ~(size_t)255);
     const size_t total = off_cand + cand_records * sizeof(TensorCand);
@@ -1219,6 +1463,7 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
     if (e != cudaSuccess) return e;
     float* band = reinterpret_cast<float*>(scratch + off_band);
     unsigned* amin = reinterpret_cast<unsigned*>(scratch + off_amin);
+    float* qscale = reinterpret_cast<float*>(scratch + off_qs);
     unsigned* common_counts = reinterpret_cast<unsigned*>(scratch + off_cnt);
     cb.cta_count = reinterpret_cast<unsigned*>(scratch + off_ccnt);
     cb.rec = reinterpret_cast<TensorCand*>(scratch + off_cand);
@@ -1229,10 +1474,6 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
                                                                       (unsigned)(g.KB * 64 + g.KS * 16), (unsigned)(gp.KB * 64 + gp.KS * 16));
     e = cudaGetLastError();
     int nl = 1;
-    // every CTA allocates all 512 TMEM columns: ask for enough shared memory that only one
-    // CTA is resident per SM even at KP = 64
-    const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
-    const size_t smem_plain = std::max(tensor_smem_bytes(gp), (size_t)120 * 1024);
     for (int b = 0; b < nbatches && e == cudaSuccess; ++b) {
         const int s0 = b * batch_strips;
         const int bs = std::min(batch_strips, strips - s0);
@@ -1241,17 +1482,7 @@ cudaError_t tensor_search(int k, int m, int n, const float* d_queries, const flo
         const float* bq = d_queries + (size_t)q0 * k;
         cb.common_count = common_counts + b;
         cb.n_ctas = (unsigned)bs * (unsigned)splits;  // the common region follows the regions actually used
-        // query image + screen in the layout the index was built in; for the k range that has two precision
-        // modes both variants are launched and the one that does not match the header word exits at once
-        dim3 grid((unsigned)bs, (unsigned)splits);
-        tensor_query_image_kernel<<<bs, rows, 0, st>>>(bq, bm, k, g, hdr, scratch, band, amin, mode_word, 0u);
-        if (modes) tensor_query_image_kernel<<<bs, rows, 0, st>>>(bq, bm, k, gp, hdr, scratch, band, amin, mode_word, 1u);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) break;
-        if (longk) e = tensor_longk_launch(g.KB, grid, st, scratch, bm, rimage, nblocks, tps, band, amin, cb);
-        else e = tensor_screen_dispatch(g, grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 0u);
-        if (e == cudaSuccess && modes)
-            e = tensor_screen_dispatch(gp, grid, smem_plain, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 1u);
+        e = screen_batch(ss, k, bq, bm, bs, splits, hdr, scratch, band, amin, qscale, rimage, nblocks, tps, cb, st);
         nl += modes ? 2 : 0;
         if (e != cudaSuccess) break;
         const int rgrid = num_sms * 8;
@@ -1370,13 +1601,12 @@ cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_querie
                                int index_base, u64* d_keys, bool exact, int num_sms, cudaStream_t st, cudaMemPool_t pool,
                                int* launches, unsigned* d_stats)
 {
-    const TensorGeom g = tensor_geom(k);
-    const TensorGeom gp = tensor_geom(k, true);
-    const bool modes = tensor_has_modes(k);
-    const unsigned* mode_word = modes ? reinterpret_cast<const unsigned*>(d_section) + THDR_MODE : nullptr;
+    const ScreenSetup ss = screen_setup(k, d_section);
+    const TensorGeom g = ss.g, gp = ss.gf;
+    const bool modes = ss.modes;
+    const unsigned* mode_word = ss.mode_word;
     const int nblocks = (n + LB - 1) / LB;
-    const bool longk = g.KB > 2;
-    const int rows = longk ? tensor_longk_rows(g.KB) : T_BM;
+    const int rows = ss.rows;
     const int strips = (m + rows - 1) / rows;
     const float* hdr = d_section;
     const unsigned char* rimage = reinterpret_cast<const unsigned char*>(d_section + TENSOR_HDR_FLOATS);
@@ -1439,7 +1669,8 @@ cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_querie
     const size_t qimg_bytes = (size_t)batch_strips * image_bytes(rows, g.KB, g.KS);
     const size_t off_band = (qimg_bytes + 255) & ~(size_t)255;
     const size_t off_amin = off_band + ((batch_queries * 4 + 255) & ~(size_t)255);
-    const size_t off_cnt = off_amin + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_qs = off_amin + ((batch_queries * 4 + 255) & ~(size_t)255);
+    const size_t off_cnt = off_qs + ((batch_queries * 4 + 255) & ~(size_t)255);
     const size_t off_ccnt = off_cnt + (((size_t)nbatches * 4 + 255) & ~(size_t)255);
     const size_t off_ecnt = off_ccnt + (((size_t)cb.n_ctas * 4 + 255) & ~(size_t)255);
     const size_t off_exact = off_ecnt + ((batch_queries * 4 + 255) & ~(size_t)255);
@@ -1450,6 +1681,7 @@ cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_querie
     if (e != cudaSuccess) return e;
     float* band = reinterpret_cast<float*>(scratch + off_band);
     unsigned* amin = reinterpret_cast<unsigned*>(scratch + off_amin);
+    float* qscale = reinterpret_cast<float*>(scratch + off_qs);
     unsigned* common_counts = reinterpret_cast<unsigned*>(scratch + off_cnt);
     unsigned* exact_count = reinterpret_cast<unsigned*>(scratch + off_ecnt);
     u64* exact_list = reinterpret_cast<u64*>(scratch + off_exact);
@@ -1461,8 +1693,6 @@ cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_querie
                                                                       (unsigned)(gp.KB * 64 + gp.KS * 16));
     e = cudaGetLastError();
     nl += 1;
-    const size_t smem = std::max(tensor_smem_bytes(g), (size_t)120 * 1024);
-    const size_t smem_plain = std::max(tensor_smem_bytes(gp), (size_t)120 * 1024);
     for (int b = 0; b < nbatches && e == cudaSuccess; ++b) {
         const int s0 = b * batch_strips;
         const int bs = std::min(batch_strips, strips - s0);
@@ -1472,18 +1702,14 @@ cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_querie
         u64* bkeys = d_keys + (size_t)q0 * K;
         cb.common_count = common_counts + b;
         cb.n_ctas = (unsigned)bs * (unsigned)splits;
-        dim3 grid((unsigned)bs, (unsigned)splits);
         e = cudaMemsetAsync(exact_count, 0, (size_t)bm * 4, st);
         if (e != cudaSuccess) break;
-        tensor_query_image_kernel<<<bs, rows, 0, st>>>(bq, bm, k, g, hdr, scratch, band, amin, mode_word, 0u);
-        if (modes) tensor_query_image_kernel<<<bs, rows, 0, st>>>(bq, bm, k, gp, hdr, scratch, band, amin, mode_word, 1u);
+        e = screen_batch(ss, k, bq, bm, bs, splits, hdr, scratch, band, amin, qscale, rimage, nblocks, tps, cb, st, true, false);
+        if (e != cudaSuccess) break;
         tensor_topk_threshold_kernel<<<(bm + 255) / 256, 256, 0, st>>>(bq, bm, k, hdr, bkeys, K, amin);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
-        if (longk) e = tensor_longk_launch(g.KB, grid, st, scratch, bm, rimage, nblocks, tps, band, amin, cb);
-        else e = tensor_screen_dispatch(g, grid, smem, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 0u);
-        if (e == cudaSuccess && modes)
-            e = tensor_screen_dispatch(gp, grid, smem_plain, st, scratch, bm, rimage, nblocks, tps, band, amin, cb, mode_word, 1u);
+        e = screen_batch(ss, k, bq, bm, bs, splits, hdr, scratch, band, amin, qscale, rimage, nblocks, tps, cb, st, false, true);
         if (e != cudaSuccess) break;
         const int rgrid = num_sms * 8;
         if (exact)

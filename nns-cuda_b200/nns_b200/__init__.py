@@ -264,7 +264,9 @@ def tensor_kp(k: int) -> int:
 def tensor_stats() -> dict:
     out = (c_uint * 4)()
     _check(lib.nns_b200_tensor_stats(out))
-    return {"candidates": int(out[0]), "overflow": int(out[1]), "capacity": int(out[2]), "kp": int(out[3])}
+    # [3]: contraction columns of the operand images the index holds | precision mode << 16 (2 = F16 operands + accumulators)
+    return {"candidates": int(out[0]), "overflow": int(out[1]), "capacity": int(out[2]), "kp": int(out[3]) & 0xFFFF,
+            "mode": "f16" if (int(out[3]) >> 16) == 2 else "bf16"}
 
 
 def index_floats(k: int, n: int) -> int:

@@ -658,14 +658,14 @@ def test_topk_matches_the_v0_form_oracle(nns, oracle, torch_mod, kind, k, m, n, 
 
 
 def test_precision_mode_probe_picks_plain_or_split_per_index(nns, oracle, torch_mod):
-    """For 10 <= k <= 42 the index build probes the data (2-NN distances of sample points vs the plain-BF16
-    error band) and builds plain BF16 operand images (a third of the tensor work) when the band is
-    selective, split-precision ones otherwise.  Uniform 16-D data -> plain (32 columns); the same points
+    """For 10 <= k <= 42 the index build probes the data (2-NN distances of sample points vs the plain-F16
+    error band) and builds plain F16 operand images (a third of the tensor work, 16-bit accumulators) when the
+    band is selective, split-precision BF16 ones otherwise.  Uniform 16-D data -> plain (32 columns); the same points
     squeezed onto a 2-D sheet inside the 16-D cube -> split (64 columns).  Both answers must be V0's."""
     torch = torch_mod
     k, m, n = 16, 2048, 400_000
     s, r = make_case("uniform", k, m, n, 71)
-    for name, want_kp in (("uniform", 32), ("sheet", 64)):
+    for name, want_kp, want_mode in (("uniform", 32, "f16"), ("sheet", 64, "bf16")):
         if name == "sheet":  # coordinates 2..15 are tiny multiples of the first two: intrinsic dimension 2
             rr, ss = r.copy(), s.copy()
             for t in range(2, k):
@@ -677,8 +677,51 @@ def test_precision_mode_probe_picks_plain_or_split_per_index(nns, oracle, torch_
         index = nns.DeviceIndex(dev(torch, rr))
         g = index.search(dev(torch, ss), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
         st = nns.tensor_stats()
-        assert st["overflow"] == 0 and st["kp"] == want_kp, (name, st)
+        assert st["overflow"] == 0 and st["kp"] == want_kp and st["mode"] == want_mode, (name, st)
         assert np.array_equal(g, v), (name, int((g != v).sum()))
+
+
+@pytest.mark.parametrize("k,m,n,kind", [(10, 700, 60_000, "uniform"), (13, 513, 50_000, "uniform"), (24, 1000, 70_000, "uniform"),
+                                        (48, 600, 40_000, "uniform"), (64, 512, 30_000, "uniform"), (100, 300, 20_000, "uniform"),
+                                        (128, 1024, 50_000, "uniform"), (126, 257, 12_345, "uniform"), (64, 400, 30_000, "scaled")])
+def test_f16_mode_matches_v0(nns, oracle, torch_mod, k, m, n, kind):
+    """Plain F16 operands with F16 accumulators (every 43 <= k <= 128 index built in one piece; 10 <= k <= 42 when the probe
+    picks it): packed TMEM loads + HMNMX2 epilogue, scores unscaled per query before they are compared.  V0's answers
+    bit for bit with V0 rounding; data far from the unit cube (coordinates ~1e4, ~1e-4) goes through the scaling."""
+    torch = torch_mod
+    s, r = make_case("uniform", k, m, n, 91)
+    if kind == "scaled":
+        s, r = (s * np.float32(2.5e4) - np.float32(7e3)).astype(np.float32), (r * np.float32(2.5e4) - np.float32(7e3)).astype(np.float32)
+        s[::3] = (s[::3] * np.float32(4.0)).astype(np.float32)  # a third of the queries well outside the reference cloud
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    index = nns.DeviceIndex(dev(torch, r))
+    g = index.search(dev(torch, s), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+    st = nns.tensor_stats()
+    assert st["overflow"] == 0 and st["mode"] == "f16", st
+    if k <= 64:
+        assert st["candidates"] < m * ((n + 31) // 32) // 2, st  # the screen screens (distances concentrate as k grows: less so)
+    assert np.array_equal(g, v), int((g != v).sum())
+    tiny = np.float32(1e-4)
+    g2 = nns.DeviceIndex(dev(torch, (r * tiny).astype(np.float32))).search(dev(torch, (s * tiny).astype(np.float32)),
+                                                                          nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+    v2, _ = oracle.v0_omp(k, m, n, (s * tiny).astype(np.float32), (r * tiny).astype(np.float32))
+    assert np.array_equal(g2, v2) and nns.tensor_stats()["mode"] == "f16"
+
+
+def test_f16_mode_reference_outside_the_sampled_radius_is_not_trusted(nns, oracle, torch_mod):
+    """The F16 scale comes from a strided block sample.  A reference 1000 cloud radii out that the sample missed would
+    overflow the 16-bit operands: the image kernel flags the section, every query then takes the exact path (all units
+    are candidates, or the FP32 kernel behind the overflow flag), and the outlier is still found by the query next to it."""
+    torch = torch_mod
+    k, m, n = 48, 300, 300_000  # 2344 blocks -> the sample takes every 3rd block
+    s, r = make_case("uniform", k, m, n, 93)
+    r[128 + 5] = np.float32(3000.0)   # block 1: not sampled
+    s[7] = np.float32(2999.5)
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    assert v[7] == 128 + 5
+    g = nns.DeviceIndex(dev(torch, r)).search(dev(torch, s), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+    assert nns.tensor_stats()["mode"] == "f16"
+    assert np.array_equal(g, v), int((g != v).sum())
 
 
 # ---- tcgen05 K-loop kernel, 128 < k <= 509 (tensor_longk.cu) ---------------------------------------

@@ -32,9 +32,43 @@ def trunc32(x64):
     return np.where(over, np.nextafter(t, F32(0)), t).astype(F32)
 
 
+def f16(x):
+    """round-to-nearest-even -> F16 (kept in an FP32 container), like __float2half_rn; subnormals, overflow -> INF"""
+    with np.errstate(over="ignore"):
+        return np.asarray(x).astype(np.float16).astype(F32)
+
+
+def f16_ref_scale(rmax_sampled):
+    """tensor_f16_ref_scale (csrc/tensor_common.cuh): power of two that brings the sampled radius to [4, 8)"""
+    if not (1e-30 < rmax_sampled < 1e30):
+        return F32(1.0)
+    _, e = np.frexp(F32(rmax_sampled))
+    return F32(np.ldexp(1.0, 3 - int(e)))
+
+
+F16_R_MAX = F32(176.0)
+
+
+def f16_query_scale(A, R):
+    """tensor_f16_query_scale: largest power of two t <= 2^8 with t R (R + 2A) <= 2^15 and 2 t A <= 2^15; 0 = unusable"""
+    A, R = F32(A), F32(R)
+    if not (A <= F32(1e30)) or not (R <= F16_R_MAX):
+        return F32(0.0)
+    lim = F32(256.0)
+    p = F32(R * F32(R + F32(2.0) * A))
+    if p > 0:
+        lim = min(lim, F32(F32(32768.0) / p))
+    if A > 0:
+        lim = min(lim, F32(F32(16384.0) / A))
+    if not (lim >= F32(6.1035156e-5)):
+        return F32(0.0)
+    _, e = np.frexp(F32(lim))
+    return F32(np.ldexp(1.0, int(e) - 1))
+
+
 def geometry(k, plain=False):
     """(contraction length, data columns): split-precision columns up to k = 42 unless the index chose the
-    plain BF16 layout (tensor_geom(k, plain) in csrc/tensor_search.cu; plain exists for 10 <= k <= 42)"""
+    plain layout (tensor_geom(k, plain) in csrc/tensor_common.cuh; plain F16 exists for 10 <= k <= 128)"""
     ndata = 3 * k if (k <= 42 and not plain) else k
     for kp in (16, 32, 64):
         if ndata + 3 <= kp:
@@ -80,11 +114,64 @@ def screen_scores(k, s, r, plain=False):
     # E(q): tensor_query_image_kernel, same FP32 operations
     r2 = rn.max()
     aa, rmax, u24 = np.sqrt(qn).astype(F32), F32(np.sqrt(r2)), F32(5.9604645e-8)
-    c_round = F32(6.2) * F32(3.8146973e-6) if split else F32(0.0078125) * F32(1.002)
+    c_round = F32(6.06) * F32(1.5258789e-5) if split else F32(0.015625) * F32(1.002)  # BF16 unit roundoff 2^-8
     E = (c_round + F32(kp) * F32(2.04) * F32(4.7683716e-7)) * aa * rmax + F32(kp + 5) * u24 * r2 + F32(kp + 8) * u24 * (aa + rmax) * (aa + rmax)
     E = (E * F32(1.05)).astype(F32)
     qn64 = (qc.astype(np.float64) ** 2).sum(axis=1)
     return acc, E, qn64
+
+
+def screen_scores_f16(k, s, r, sample_step=5):
+    """(S~ [m][n] unscaled, E [m], |q'|^2 exact [m], usable [m]) in the F16 mode (THDR_MODE = 2): F16 operands scaled by
+    powers of two, F16 accumulator re-rounded (to nearest, as measured on B200: tools/ubench_f16acc.cu) after every
+    16-column MMA step; the reference scale comes from a SAMPLE of the references (every sample_step-th), as in the
+    index build, so the true radius may exceed what the scale was chosen for."""
+    kp, ndata = geometry(k, True)
+    c = (r.astype(F32).sum(axis=0, dtype=F32) / F32(len(r))).astype(F32)
+    qc = (s - c).astype(F32)
+    rc = (r - c).astype(F32)
+    rn = np.zeros(len(r), F32)
+    for t in range(k):
+        rn = (rc[:, t].astype(np.float64) * rc[:, t].astype(np.float64) + rn.astype(np.float64)).astype(F32)
+    qn = np.zeros(len(s), F32)
+    for t in range(k):
+        qn = (qc[:, t].astype(np.float64) * qc[:, t].astype(np.float64) + qn.astype(np.float64)).astype(F32)
+    r2 = rn.max()
+    aa, rmax = np.sqrt(qn).astype(F32), F32(np.sqrt(r2))
+    sc = f16_ref_scale(F32(np.sqrt(rn[::sample_step].max())))
+    tq = np.array([f16_query_scale(F32(sc * a), F32(sc * rmax)) for a in aa], F32)
+    flagged = bool(((rn * sc * sc) > F16_R_MAX * F16_R_MAX).any())  # tensor_ref_image_kernel: out-of-range reference
+    usable = (tq > 0) & (not flagged)
+    tt = np.where(tq > 0, tq, F32(1.0)).astype(F32)
+    norm_col = kp - 16 if kp in (80, 144) else ndata  # tensor_geom: the norm columns get their own step when the data fills the blocks
+    A = np.zeros((len(s), kp), F32)
+    B = np.zeros((len(r), kp), F32)
+    A[:, :k] = f16((F32(-2.0) * tt * sc)[:, None] * qc)
+    B[:, :k] = f16(sc * rc)
+    nv = (rn * sc * sc).astype(F32)
+    n_hi = f16(nv)
+    rem = (nv - n_hi).astype(F32)
+    n_mid = f16(rem)
+    n_lo = f16((rem - n_mid).astype(F32))
+    A[:, norm_col:norm_col + 3] = f16(tt)[:, None]
+    B[:, norm_col], B[:, norm_col + 1], B[:, norm_col + 2] = n_hi, n_mid, n_lo
+    acc = np.zeros((len(s), len(r)), np.float64)
+    with np.errstate(over="ignore", invalid="ignore"):
+        for st in range(kp // 16):  # one MMA instruction: exact sum of 16 products + accumulator, rounded to F16
+            blk = A[:, 16 * st:16 * st + 16].astype(np.float64) @ B[:, 16 * st:16 * st + 16].astype(np.float64).T
+            acc = (acc + blk).astype(np.float16).astype(np.float64)
+    uq = (tt * sc * sc).astype(np.float64)
+    S = acc / uq[:, None]
+    # E(q): tensor_error_bound_f16, same FP32 operations
+    u24, u11 = F32(5.9604645e-8), F32(4.8828125e-4)
+    steps = kp // 16
+    big = rmax * rmax + F32(2.0) * aa * rmax
+    sub = (F32(np.sqrt(F32(k))) * (F32(2.0) * tt * sc * aa + sc * rmax) + F32(steps + 3)) * F32(2.9802322e-8) / (tt * sc * sc)
+    E = (F32(2.0) * u11 * F32(1.001) + F32(kp) * F32(2.04) * F32(4.7683716e-7)) * aa * rmax + F32(steps) * u11 * F32(1.016) * F32(1.002) * big + sub \
+        + F32(kp + 5) * u24 * r2 + F32(kp + 8) * u24 * (aa + rmax) * (aa + rmax)
+    E = (E * F32(1.05)).astype(F32)
+    qn64 = (qc.astype(np.float64) ** 2).sum(axis=1)
+    return S, E, qn64, usable
 
 
 def v0_distances(s, r):
@@ -99,10 +186,10 @@ def v0_distances(s, r):
 CASES = ["uniform", "clustered", "offset1000", "scale1e-3", "mixed", "one_outlier"]
 
 
-@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, 129, 200, 320, 509, -10, -16, -29, -30, -42])
+@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, 129, 200, 320, 509, -10, -13, -16, -29, -30, -42, -61, -64, -100, -128])
 @pytest.mark.parametrize("case", CASES)
 def test_screen_error_stays_inside_the_band(k, case):
-    plain, k = k < 0, abs(k)  # negative = the plain BF16 layout of a k that also has the split one
+    plain, k = k < 0, abs(k)  # negative = the plain F16 mode (10 <= k <= 128)
     m, n = 48, 1536
     if case == "clustered" and k == 3:
         s, r = make_case("clustered", k, m, n, 11)
@@ -119,8 +206,16 @@ def test_screen_error_stays_inside_the_band(k, case):
     elif case == "one_outlier":
         r[3] = 300.0
     s, r = s.astype(F32), r.astype(F32)
-    acc, E, qn64 = screen_scores(k, s, r, plain)
     d = v0_distances(s, r).astype(np.float64)
+    if plain:
+        acc, E, qn64, usable = screen_scores_f16(k, s, r)
+        if case == "one_outlier":  # the sample misses the outlier, the scale is 300x off: the section must be flagged, not trusted
+            assert not usable.any()
+            return
+        assert usable.all()
+        assert np.isfinite(acc).all()  # no operand, no partial sum overflowed
+    else:
+        acc, E, qn64 = screen_scores(k, s, r, plain)
     err = np.abs(acc.astype(np.float64) + qn64[:, None] - d)
     worst = (err / E[:, None].astype(np.float64)).max()
     assert worst <= 1.0, f"screen error reaches {worst:.3f} x E"
@@ -130,7 +225,7 @@ def test_screen_error_stays_inside_the_band(k, case):
 
 
 @pytest.mark.parametrize("k,case", [(3, "uniform"), (3, "clustered"), (16, "uniform"), (16, "mixed"), (128, "uniform"), (64, "offset1000"),
-                                    (-16, "uniform"), (-16, "mixed"), (-30, "offset1000")])
+                                    (-16, "uniform"), (-16, "mixed"), (-30, "offset1000"), (-128, "uniform"), (-64, "clustered")])
 def test_screen_and_rescore_logic_returns_v0(k, case):
     """The screen's control logic on top of the emulated scores, as the kernels run it: per query a
     running minimum over 32-reference units in index order, a unit is recorded when its minimum is
@@ -149,7 +244,12 @@ def test_screen_and_rescore_logic_returns_v0(k, case):
         if case == "mixed":
             r = r.copy()
             r[::7] *= F32(50.0)
-    acc, E, _ = screen_scores(k, s, r, plain)
+    if plain:
+        acc, E, _, usable = screen_scores_f16(k, s, r)
+        assert usable.all()
+        acc = acc.astype(F32)  # the epilogue unscales in FP32 (exact: powers of two)
+    else:
+        acc, E, _ = screen_scores(k, s, r, plain)
     d = v0_distances(s, r)
     v0 = d.argmin(axis=1)  # numpy argmin = first minimum = V0's strict '>' update (core.cu:44)
     band = (F32(2.0) * E).astype(F32)

@@ -33,6 +33,7 @@ for i in range(32):
     ws = " ".join(f"{int(out[24 + e][i] - mi):5d}" for e in range(0, 8, 2))
     rd = " ".join(f"{int(out[4 + e][i] - mi):5d}" for e in range(0, 8, 2))
     rl = " ".join(f"{int(out[12 + e][i] - mi):5d}" for e in range(0, 8, 2))
-    print(f"{i:4d} {mi - t0:8d} | wait {ws} | ready {rd} | released {rl}")
+    iss = f"{int(out[1][i] - mi):5d} {int(out[2][i] - mi):5d}"  # the issuer: started waiting for the buffer / got it (and the B stage)
+    print(f"{i:4d} {mi - t0:8d} | issuer wait-start, go {iss} | wait {ws} | ready {rd} | released {rl}")
 d = np.diff(out[3])
 print("MMA issue period per unit: median %.0f clk, mean %.0f" % (np.median(d), d.mean()))
