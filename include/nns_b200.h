@@ -197,7 +197,8 @@ int nns_b200_plan(int k, int m, int n, unsigned flags, int num_sms, int *plan);
 /* diagnostics of the last tensor-path search on the current device (synchronises the device):
  * out4 = { (query, 32-reference unit) candidates emitted by the tcgen05 screen, 1 if the candidate
  * buffer overflowed and the FP32 kernel launched behind it redid the search, candidate capacity of a
- * query batch, contraction length (BF16 columns) of the operand images the index chose } */
+ * query batch, contraction length (16-bit columns) of the operand images the index holds | precision mode << 16
+ * (0 = BF16 operands with FP32 accumulators, 2 = F16 operands with F16 accumulators) } */
 int nns_b200_tensor_stats(unsigned *out4);
 
 /* number of kernels of this library launched by this process so far (bench.py's gpu_launches) */
