@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <vector>
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -196,8 +198,70 @@ static void probe(int ab_bf16, int c_f32, int second, int pattern)
     cudaFree(d_a); cudaFree(d_b); cudaFree(d_raw); cudaFree(d_p);
 }
 
-int main()
+// (C) is an F16-accumulator MMA instruction "exact sum of the 16 products and the accumulator, rounded to nearest"?
+// Random F16 operands (mixed magnitudes, both signs), one overwriting + `second` accumulating instructions, every
+// accumulator compared BIT FOR BIT with that model evaluated in FP64 on the host.
+static double round_to_f16(double x)  // round to nearest even, F16 normal / subnormal grid, no double rounding
 {
+    if (x == 0.0 || !std::isfinite(x)) return x;
+    int e;
+    std::frexp(x, &e);                // |x| = f * 2^e, f in [0.5, 1)
+    int q = e - 11;                   // ulp exponent for 11 significant bits
+    if (q < -24) q = -24;             // subnormal grid 2^-24
+    const double r = std::nearbyint(std::ldexp(x, -q));  // default rounding mode: to nearest even
+    const double y = std::ldexp(r, q);
+    return std::fabs(y) > 65504.0 ? std::copysign(INFINITY, x) : y;
+}
+static void model_check(int second, unsigned seed)
+{
+    std::vector<float> A(128 * 16), B(64 * 16);
+    srand(seed);
+    auto rnd = [&]() {
+        const double u = (rand() / (double)RAND_MAX) * 2.0 - 1.0;
+        const int sh = rand() % 12;   // magnitudes over 12 binades
+        return (float)std::ldexp(u, -sh + 3);
+    };
+    for (auto& v : A) v = f16_f(h_f16(rnd()));
+    for (auto& v : B) v = f16_f(h_f16(rnd()));
+    std::vector<unsigned short> a(A.size()), b(B.size());
+    for (size_t i = 0; i < a.size(); ++i) a[i] = h_f16(A[i]);
+    for (size_t i = 0; i < b.size(); ++i) b[i] = h_f16(B[i]);
+    unsigned short *d_a, *d_b; uint32_t *d_raw, *d_p;
+    CK(cudaMalloc(&d_a, a.size() * 2)); CK(cudaMalloc(&d_b, b.size() * 2));
+    CK(cudaMalloc(&d_raw, 128 * 64 * 4)); CK(cudaMalloc(&d_p, 128 * 32 * 4));
+    CK(cudaMemcpy(d_a, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_b, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+    mma_probe<<<1, 128>>>(d_a, d_b, 0, 0, second, d_raw, d_p);
+    CK(cudaDeviceSynchronize());
+    std::vector<uint32_t> raw(128 * 64);
+    CK(cudaMemcpy(raw.data(), d_raw, raw.size() * 4, cudaMemcpyDeviceToHost));
+    long mism = 0, off_by_one_toward_zero = 0;
+    double worst_rel = 0;
+    for (int r = 0; r < 128; ++r)
+        for (int c = 0; c < 64; ++c) {
+            double dot = 0;
+            for (int j = 0; j < 16; ++j) dot += (double)A[r * 16 + j] * (double)B[c * 16 + j];  // exact: 22-bit products, 16 terms
+            double acc = round_to_f16(dot);
+            for (int i = 0; i < second; ++i) acc = round_to_f16(acc + dot);
+            const float got = f16_f((unsigned short)(raw[r * 64 + c] & 0xffff));
+            if ((double)got != acc) {
+                ++mism;
+                if (std::fabs((double)got) < std::fabs(acc)) ++off_by_one_toward_zero;
+                if (acc != 0) worst_rel = std::max(worst_rel, std::fabs(((double)got - acc) / acc));
+                if (mism <= 5) printf("   mismatch r%d c%d: model %.9g hardware %.9g (exact %.12g)\n", r, c, acc, (double)got, dot * (1 + second));
+            }
+        }
+    printf("[model] %d accumulating repeats, seed %u: %ld of 8192 accumulators differ from round-to-nearest(exact sum) (%ld smaller in magnitude), worst relative difference %.3g\n",
+           second, seed, mism, off_by_one_toward_zero, worst_rel);
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_raw); cudaFree(d_p);
+}
+
+int main(int argc, char** argv)
+{
+    if (argc > 1) {  // model check only
+        for (unsigned seed = 1; seed <= 4; ++seed) { model_check(0, seed); model_check(1, seed); model_check(3, seed); }
+        return 0;
+    }
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     for (int w : {16, 32}) {
