@@ -28,6 +28,11 @@ constexpr int T_MAX_STAGES = 24;  // upper bound of the B ring depth (the mbarri
 #ifndef NNS_T_SPIN_F16
 #define NNS_T_SPIN_F16 0    // the same for the F16 screens: three polling issuers cost more (power-capped clock) than their wake-up saves
 #endif
+#ifndef NNS_T_EPI_NORM
+#define NNS_T_EPI_NORM 0    // F16 mode, k = 62..64 / 126..128: 1 = the epilogue adds |r'|^2 (no norm columns, one MMA step less).
+                            // Measured on C4 (k = 128, power-capped at 1 kW): 232 ms at 1.49 GHz vs 229 ms at 1.55 GHz with the norm
+                            // columns -- the MMA step saved is paid back in clock, so it stays off; parity-tested in both settings
+#endif
 #ifndef NNS_T_PIPE
 #define NNS_T_PIPE 2        // epilogue of the 64-reference units: 0 = one unit per loop trip, a candidate test per 32-column chunk;
 #endif                      // 2 = NNS_T_TRIP units per trip and ONE test per trip (12 % faster on C2: profiles/r2_tune_trip.txt);
@@ -159,6 +164,12 @@ __device__ __forceinline__ uint32_t hmin2(uint32_t a, uint32_t b)  // HMNMX2: pe
     asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c)  // HFMA2: a * b + c per half, one rounding
+{
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ float hmin2_to_float(uint32_t a)  // the smaller half, exactly, as FP32
 {
     float lo, hi;
@@ -273,13 +284,22 @@ __device__ __forceinline__ size_t image_chunk_offset(int rows, int row, int kb, 
 // all: for k <= 4 the 3k split-precision columns and the norm fit ONE K = 16 MMA step.
 struct TensorGeom {
     int KB, KS, norm_col, ndata, split;
+    int en;   // F16 mode, k = 62..64 / 126..128: |r'|^2 is added by the epilogue instead of a sixteen-column MMA step of its own
 };
 // plain = single BF16 column per dimension even where the split-precision layout exists (see "Precision mode")
 __host__ __device__ inline TensorGeom tensor_geom(int k, bool plain = false)
 {
     TensorGeom g;
+    g.en = 0;
     g.split = (k <= TENSOR_SPLIT_MAX_K && !plain) ? 1 : 0;
     g.ndata = g.split ? 3 * k : k;
+    // F16 mode (`plain` = the F16 layout): where the data columns fill the 64-column blocks exactly, the three norm
+    // columns would cost a whole extra K = 16 step (k = 128: 9 instead of 8).  The 16-bit epilogue has the slack to add
+    // t * s^2 |r'|^2 itself (one HFMA2 per two columns, on the otherwise idle FMA pipe): no norm columns at all.
+    if (plain && NNS_T_EPI_NORM && ((g.ndata > 61 && g.ndata <= 64) || (g.ndata > 125 && g.ndata <= 128))) {
+        g.KB = g.ndata <= 64 ? 1 : 2; g.KS = 0; g.norm_col = -100; g.en = 1;
+        return g;
+    }
     // the three norm columns ride in the last block whenever it has room for them
     if (g.ndata + 3 <= 16) { g.KB = 0; g.KS = 1; g.norm_col = g.ndata; }
     else if (g.ndata + 3 <= 32) { g.KB = 0; g.KS = 2; g.norm_col = g.ndata; }
@@ -358,14 +378,15 @@ __host__ __device__ inline float tensor_f16_query_scale(float A, float R)  // 0 
     (void)f;
     return ldexpf(1.0f, e - 1);       // largest power of two <= lim
 }
-__host__ __device__ inline float tensor_error_bound_f16(int KP, int k, float a, float rmax, float s, float t)
+// en: the norm is a single F16 number (u11 rmax^2) added by one HFMA2 in the epilogue (one more rounding of the full sum)
+__host__ __device__ inline float tensor_error_bound_f16(int KP, int k, float a, float rmax, float s, float t, bool en = false)
 {
     const float u24 = 5.9604645e-8f, u11 = 4.8828125e-4f;
-    const int steps = KP / 16;
+    const int steps = KP / 16 + (en ? 1 : 0);
     const float big = rmax * rmax + 2.0f * a * rmax;
     const float sub = (sqrtf((float)k) * (2.0f * t * s * a + s * rmax) + (float)(steps + 3)) * 2.9802322e-8f / (t * s * s);
     const float E = (2.0f * u11 * 1.001f + (float)KP * 2.04f * 4.7683716e-7f) * a * rmax + (float)steps * u11 * 1.016f * 1.002f * big + sub +
-                    (KP + 5) * u24 * rmax * rmax + (KP + 8) * u24 * (a + rmax) * (a + rmax);
+                    (en ? u11 * 1.001f * rmax * rmax : 0.0f) + (KP + 5) * u24 * rmax * rmax + (KP + 8) * u24 * (a + rmax) * (a + rmax);
     return E * 1.05f;
 }
 

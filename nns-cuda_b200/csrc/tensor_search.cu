@@ -202,6 +202,10 @@ tensor_ref_image_kernel(const float* __restrict__ blocks, const int n, const int
         const size_t o = img_off + image_chunk_at(T_BN, g.KB, row, ch);
         for (int d = 0; d < dst.count; ++d) *reinterpret_cast<uint4*>(dst.p[d] + o) = *reinterpret_cast<const uint4*>(v);
     }
+    if (g.en) {  // the norm as ONE F16 number per reference, in an array behind all tile images (read by the screen's epilogue)
+        const size_t noff = (size_t)((n + T_BN - 1) / T_BN) * image_bytes(T_BN, g.KB, g.KS) + (size_t)j * 2;
+        for (int d = 0; d < dst.count; ++d) *reinterpret_cast<unsigned short*>(dst.p[d] + noff) = n_hi;
+    }
     unsigned bits = (valid && rn < inf_f()) ? __float_as_uint(rn) : 0u;  // NaN / INF norms excluded
     bits = __reduce_max_sync(0xffffffffu, bits);
     if ((threadIdx.x & 31) == 0 && bits) atomicMax(reinterpret_cast<unsigned*>(hdr) + max_word, bits);
@@ -254,7 +258,7 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
     }
     if (valid) {
         // E(q) >= |S~ - S| + |d_V0 - D'| for every reference: tensor_error_bound / tensor_error_bound_f16 (tensor_common.cuh)
-        const float E = f16 ? tensor_error_bound_f16(KP, k, a, rmax, s, tq > 0.0f ? tq : 1.0f) : tensor_error_bound(g.split != 0, KP, a, rmax);
+        const float E = f16 ? tensor_error_bound_f16(KP, k, a, rmax, s, tq > 0.0f ? tq : 1.0f, g.en != 0) : tensor_error_bound(g.split != 0, KP, a, rmax);
         const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[THDR_FLAGS] & 1u) != 0;  // NaN / INF / huge / out-of-range references
         const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f) && (tq > 0.0f);  // false for NaN too
         band[q] = usable ? 2.0f * E : inf_f();
@@ -294,13 +298,17 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
 // ~300 / TEAMS clk; the 16-bit epilogue needs 60 registers, which leaves room for a third team (28 warps, 72 registers).
 constexpr int screen_max_regs(int iss, int teams) { return (16384 / (32 * ((1 + iss + teams * T_TEAM_WARPS + 3) / 4))) & ~7; }  // registers are per scheduler
 __host__ __device__ constexpr int screen_lcm(int a, int b) { int x = a; while (x % b) x += a; return x; }
-template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS, int ISS, bool F16, int TEAMS>
+// EN (F16 only) = the images carry no norm columns: the epilogue adds t * s^2 |r'|^2 from rnorm[reference] (one F16 per
+// reference, read through L1 -- every thread of a warp reads the same 16 bytes) with one HFMA2 per two columns.
+template <int KB, int KS, int T_STAGES, int G, int SUB, int NBUF, bool TS, int ISS, bool F16, int TEAMS, bool EN>
 __global__ void __maxnreg__(screen_max_regs(ISS, TEAMS))
 tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, const unsigned char* __restrict__ rimage,
                      const int ntiles, const int tiles_per_split,
                      const float* __restrict__ band, unsigned* __restrict__ approx_min, const float* __restrict__ qscale,
+                     const unsigned short* __restrict__ rnorm,
                      const CandBuf cb, const unsigned* __restrict__ mode_word, const unsigned my_mode)
 {
+    static_assert(!EN || F16, "the epilogue adds the norm only in the F16 mode");
     if (tensor_mode_mismatch(mode_word, my_mode)) return;  // the other precision variant of this launch pair runs
     // KB 64-column swizzled blocks (one 128-byte swizzle row each), then KS interleaved 16-column steps
     constexpr uint32_t A_MAIN = KB * T_BM * 128, B_MAIN = KB * T_BN * 128;
@@ -637,6 +645,12 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
             const int nunits = nt * SUB;
             const float uq = (q < m) ? __ldg(qscale + q) : 1.0f, inv_uq = 1.0f / uq;  // powers of two
             float thresh_s = thresh * uq;            // the threshold in accumulator units
+            uint32_t tq2 = 0u;                       // EN: (t, t) as F16, t = u_q / s^2 -- the weight of s^2 |r'|^2 in this row
+            if constexpr (EN) {
+                const float s = reinterpret_cast<const float*>(mode_word)[THDR_SCALE - THDR_MODE];
+                const unsigned short th = __half_as_ushort(__float2half_rn(uq / (s * s)));
+                tq2 = (uint32_t)th | ((uint32_t)th << 16);
+            }
             auto hmin16 = [&](const int o) -> uint32_t {
                 uint32_t c0 = hmin2(w[o + 0], w[o + 1]), c1 = hmin2(w[o + 2], w[o + 3]), c2 = hmin2(w[o + 4], w[o + 5]), c3 = hmin2(w[o + 6], w[o + 7]);
                 c0 = hmin2(c0, w[o + 8]); c1 = hmin2(c1, w[o + 9]); c2 = hmin2(c2, w[o + 10]); c3 = hmin2(c3, w[o + 11]);
@@ -682,7 +696,22 @@ tensor_screen_kernel(const unsigned char* __restrict__ qimage, const int m, cons
 #pragma unroll
                     for (int gq = 0; gq < GPU_; ++gq) {
                         tmem_ld64_pack16(lane_base + (uint32_t)(buf * 2 * SN + gq * 64), w);
+                        uint4 nv[EN ? 8 : 1];
+                        if constexpr (EN) {  // the 64 norms of these columns: issued under the TMEM load
+                            const uint4* np = reinterpret_cast<const uint4*>(rnorm + ((size_t)(t0 + uj / SUB) * T_BN + (size_t)((uj % SUB) * SN + gq * 64)));
+#pragma unroll
+                            for (int i4 = 0; i4 < 8; ++i4) nv[i4] = __ldg(np + i4);
+                        }
                         tmem_ld_wait();
+                        if constexpr (EN) {
+#pragma unroll
+                            for (int i4 = 0; i4 < 8; ++i4) {
+                                w[4 * i4 + 0] = hfma2(tq2, nv[i4].x, w[4 * i4 + 0]);
+                                w[4 * i4 + 1] = hfma2(tq2, nv[i4].y, w[4 * i4 + 1]);
+                                w[4 * i4 + 2] = hfma2(tq2, nv[i4].z, w[4 * i4 + 2]);
+                                w[4 * i4 + 3] = hfma2(tq2, nv[i4].w, w[4 * i4 + 3]);
+                            }
+                        }
                         if (gq == GPU_ - 1) {  // every TMEM read of this warp for the unit has completed
                             tc_fence_before();
                             __syncwarp();
@@ -1240,15 +1269,17 @@ static size_t tensor_smem_bytes(const TensorGeom& g)
            (2 * T_MAX_STAGES + 8) * 8 + 16;
 }
 
-template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS, int ISS, bool F16, int TEAMS = T_TEAMS>
+template <int KB, int KS, int STAGES, int G, int SUB, int NBUF, bool TS, int ISS, bool F16, int TEAMS = T_TEAMS, bool EN = false>
 static cudaError_t tensor_screen_launch(dim3 grid, size_t smem, cudaStream_t st, const unsigned char* qimage, int m,
                                         const unsigned char* rimage, int ntiles, int tps, const float* band, unsigned* amin,
                                         const float* qscale, const CandBuf& cb, const unsigned* mode_word, unsigned my_mode)
 {
-    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS, F16, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS, F16, TEAMS, EN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS, F16, TEAMS><<<grid, 32 * (1 + ISS + TEAMS * T_TEAM_WARPS), smem, st>>>(
-        qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode);
+    // EN: the norm array follows the tile images of the whole section
+    const unsigned short* rnorm = EN ? reinterpret_cast<const unsigned short*>(rimage + (size_t)ntiles * image_bytes(T_BN, KB, KS)) : nullptr;
+    tensor_screen_kernel<KB, KS, STAGES, G, SUB, NBUF, TS, ISS, F16, TEAMS, EN><<<grid, 32 * (1 + ISS + TEAMS * T_TEAM_WARPS), smem, st>>>(
+        qimage, m, rimage, ntiles, tps, band, amin, qscale, rnorm, cb, mode_word, my_mode);
     return cudaGetLastError();
 }
 
@@ -1277,6 +1308,13 @@ static cudaError_t tensor_screen_dispatch_t(const TensorGeom& g, dim3 grid, size
     } else {
         if (g.KB == 0 && g.KS == 1) return NNS_SCREEN_ISS(0, 1, 6, 4, NNS_T_SUB, 2 * NNS_T_SUB, false, ISS_);
         if (g.KB == 0) return NNS_SCREEN_ISS(0, 2, 6, 2, NNS_T_SUB, 2 * NNS_T_SUB, false, ISS_);
+    }
+    if constexpr (F16) {
+        if (g.en) {  // k = 62..64 / 126..128: no norm columns, the epilogue adds |r'|^2
+            if (g.KB == 1)
+                return tensor_screen_launch<1, 0, 8, 1, 2, 3, true, 1, true, T_TEAMS, true>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode);
+            return tensor_screen_launch<2, 0, 4, 1, 1, 2, false, 1, true, T_TEAMS, true>(grid, smem, st, qimage, m, rimage, ntiles, tps, band, amin, qscale, cb, mode_word, my_mode);
+        }
     }
 #if NNS_T_TS == 1
     // measured on B200 (profiles/r2_tune_ts.txt): A in TMEM + three 64-reference buffers is 3 % faster at 64

@@ -683,11 +683,14 @@ def test_precision_mode_probe_picks_plain_or_split_per_index(nns, oracle, torch_
 
 @pytest.mark.parametrize("k,m,n,kind", [(10, 700, 60_000, "uniform"), (13, 513, 50_000, "uniform"), (24, 1000, 70_000, "uniform"),
                                         (48, 600, 40_000, "uniform"), (64, 512, 30_000, "uniform"), (100, 300, 20_000, "uniform"),
-                                        (128, 1024, 50_000, "uniform"), (126, 257, 12_345, "uniform"), (64, 400, 30_000, "scaled")])
+                                        (128, 1024, 50_000, "uniform"), (126, 257, 12_345, "uniform"), (64, 400, 30_000, "scaled"),
+                                        (62, 300, 9_000, "uniform"), (61, 300, 9_000, "uniform"), (125, 260, 7_000, "uniform"),
+                                        (128, 300, 20_000, "scaled")])
 def test_f16_mode_matches_v0(nns, oracle, torch_mod, k, m, n, kind):
     """Plain F16 operands with F16 accumulators (every 43 <= k <= 128 index built in one piece; 10 <= k <= 42 when the probe
     picks it): packed TMEM loads + HMNMX2 epilogue, scores unscaled per query before they are compared.  V0's answers
-    bit for bit with V0 rounding; data far from the unit cube (coordinates ~1e4, ~1e-4) goes through the scaling."""
+    bit for bit with V0 rounding; data far from the unit cube (coordinates ~1e4, ~1e-4) goes through the scaling.
+    (k = 62..64 and 126..128 are the shapes of the NNS_T_EPI_NORM build variant: no norm columns, the epilogue adds |r'|^2.)"""
     torch = torch_mod
     s, r = make_case("uniform", k, m, n, 91)
     if kind == "scaled":
@@ -698,7 +701,7 @@ def test_f16_mode_matches_v0(nns, oracle, torch_mod, k, m, n, kind):
     g = index.search(dev(torch, s), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
     st = nns.tensor_stats()
     assert st["overflow"] == 0 and st["mode"] == "f16", st
-    if k <= 64:
+    if k <= 64 and n >= 30_000:  # (small n: every reference split of a strip seeds its own candidates)
         assert st["candidates"] < m * ((n + 31) // 32) // 2, st  # the screen screens (distances concentrate as k grows: less so)
     assert np.array_equal(g, v), int((g != v).sum())
     tiny = np.float32(1e-4)

@@ -66,10 +66,16 @@ def f16_query_scale(A, R):
     return F32(np.ldexp(1.0, int(e) - 1))
 
 
-def geometry(k, plain=False):
+EPI_NORM = False  # NNS_T_EPI_NORM of the build (csrc/tensor_common.cuh); the emulation of the variant is tested either way
+
+
+def geometry(k, plain=False, en=None):
     """(contraction length, data columns): split-precision columns up to k = 42 unless the index chose the
     plain layout (tensor_geom(k, plain) in csrc/tensor_common.cuh; plain F16 exists for 10 <= k <= 128)"""
     ndata = 3 * k if (k <= 42 and not plain) else k
+    en = EPI_NORM if en is None else en
+    if plain and en and (61 < ndata <= 64 or 125 < ndata <= 128):  # F16 mode: no norm columns, the epilogue adds |r'|^2 (TensorGeom::en)
+        return (64 if ndata <= 64 else 128), ndata
     for kp in (16, 32, 64):
         if ndata + 3 <= kp:
             return kp, ndata
@@ -121,12 +127,12 @@ def screen_scores(k, s, r, plain=False):
     return acc, E, qn64
 
 
-def screen_scores_f16(k, s, r, sample_step=5):
+def screen_scores_f16(k, s, r, sample_step=5, epi_norm=None):
     """(S~ [m][n] unscaled, E [m], |q'|^2 exact [m], usable [m]) in the F16 mode (THDR_MODE = 2): F16 operands scaled by
     powers of two, F16 accumulator re-rounded (to nearest, as measured on B200: tools/ubench_f16acc.cu) after every
     16-column MMA step; the reference scale comes from a SAMPLE of the references (every sample_step-th), as in the
     index build, so the true radius may exceed what the scale was chosen for."""
-    kp, ndata = geometry(k, True)
+    kp, ndata = geometry(k, True, epi_norm)
     c = (r.astype(F32).sum(axis=0, dtype=F32) / F32(len(r))).astype(F32)
     qc = (s - c).astype(F32)
     rc = (r - c).astype(F32)
@@ -143,6 +149,7 @@ def screen_scores_f16(k, s, r, sample_step=5):
     flagged = bool(((rn * sc * sc) > F16_R_MAX * F16_R_MAX).any())  # tensor_ref_image_kernel: out-of-range reference
     usable = (tq > 0) & (not flagged)
     tt = np.where(tq > 0, tq, F32(1.0)).astype(F32)
+    en = ndata + 3 > kp  # no room for norm columns: one F16 norm per reference, added by an HFMA2 in the epilogue
     norm_col = kp - 16 if kp in (80, 144) else ndata  # tensor_geom: the norm columns get their own step when the data fills the blocks
     A = np.zeros((len(s), kp), F32)
     B = np.zeros((len(r), kp), F32)
@@ -153,22 +160,25 @@ def screen_scores_f16(k, s, r, sample_step=5):
     rem = (nv - n_hi).astype(F32)
     n_mid = f16(rem)
     n_lo = f16((rem - n_mid).astype(F32))
-    A[:, norm_col:norm_col + 3] = f16(tt)[:, None]
-    B[:, norm_col], B[:, norm_col + 1], B[:, norm_col + 2] = n_hi, n_mid, n_lo
+    if not en:
+        A[:, norm_col:norm_col + 3] = f16(tt)[:, None]
+        B[:, norm_col], B[:, norm_col + 1], B[:, norm_col + 2] = n_hi, n_mid, n_lo
     acc = np.zeros((len(s), len(r)), np.float64)
     with np.errstate(over="ignore", invalid="ignore"):
         for st in range(kp // 16):  # one MMA instruction: exact sum of 16 products + accumulator, rounded to F16
             blk = A[:, 16 * st:16 * st + 16].astype(np.float64) @ B[:, 16 * st:16 * st + 16].astype(np.float64).T
             acc = (acc + blk).astype(np.float16).astype(np.float64)
+        if en:  # HFMA2: t * N + acc, one rounding
+            acc = (acc + np.outer(f16(tt).astype(np.float64), n_hi.astype(np.float64))).astype(np.float16).astype(np.float64)
     uq = (tt * sc * sc).astype(np.float64)
     S = acc / uq[:, None]
     # E(q): tensor_error_bound_f16, same FP32 operations
     u24, u11 = F32(5.9604645e-8), F32(4.8828125e-4)
-    steps = kp // 16
+    steps = kp // 16 + (1 if en else 0)
     big = rmax * rmax + F32(2.0) * aa * rmax
     sub = (F32(np.sqrt(F32(k))) * (F32(2.0) * tt * sc * aa + sc * rmax) + F32(steps + 3)) * F32(2.9802322e-8) / (tt * sc * sc)
     E = (F32(2.0) * u11 * F32(1.001) + F32(kp) * F32(2.04) * F32(4.7683716e-7)) * aa * rmax + F32(steps) * u11 * F32(1.016) * F32(1.002) * big + sub \
-        + F32(kp + 5) * u24 * r2 + F32(kp + 8) * u24 * (aa + rmax) * (aa + rmax)
+        + (u11 * F32(1.001) * rmax * rmax if en else F32(0.0)) + F32(kp + 5) * u24 * r2 + F32(kp + 8) * u24 * (aa + rmax) * (aa + rmax)
     E = (E * F32(1.05)).astype(F32)
     qn64 = (qc.astype(np.float64) ** 2).sum(axis=1)
     return S, E, qn64, usable
@@ -186,7 +196,7 @@ def v0_distances(s, r):
 CASES = ["uniform", "clustered", "offset1000", "scale1e-3", "mixed", "one_outlier"]
 
 
-@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, 129, 200, 320, 509, -10, -13, -16, -29, -30, -42, -61, -64, -100, -128])
+@pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, 129, 200, 320, 509, -10, -13, -16, -29, -30, -42, -61, -62, -64, -100, -125, -126, -128])
 @pytest.mark.parametrize("case", CASES)
 def test_screen_error_stays_inside_the_band(k, case):
     plain, k = k < 0, abs(k)  # negative = the plain F16 mode (10 <= k <= 128)
@@ -222,6 +232,27 @@ def test_screen_error_stays_inside_the_band(k, case):
     # the bound must also be worth something: on the unit cube E is a small fraction of the spread of distances
     if case == "uniform":
         assert (E.astype(np.float64) < 0.05 * d.max(axis=1)).all()
+
+
+@pytest.mark.parametrize("k", [62, 64, 126, 128])
+@pytest.mark.parametrize("case", ["uniform", "offset1000", "scale1e-3", "mixed"])
+def test_epilogue_norm_variant_stays_inside_the_band(k, case):
+    """NNS_T_EPI_NORM = 1: no norm columns, one F16 norm per reference added by an HFMA2 in the epilogue"""
+    s, r = make_case("uniform", k, 32, 1024, 13)
+    s, r = s.astype(np.float64), r.astype(np.float64)
+    if case == "offset1000":
+        s, r = s + 1000.0, r + 1000.0
+    elif case == "scale1e-3":
+        s, r = s * 1e-3, r * 1e-3
+    elif case == "mixed":
+        r[::7] *= 50.0
+        s[::5] *= 0.01
+    s, r = s.astype(F32), r.astype(F32)
+    acc, E, qn64, usable = screen_scores_f16(k, s, r, epi_norm=True)
+    assert usable.all() and np.isfinite(acc).all()
+    d = v0_distances(s, r).astype(np.float64)
+    worst = (np.abs(acc + qn64[:, None] - d) / E[:, None].astype(np.float64)).max()
+    assert worst <= 1.0, f"screen error reaches {worst:.3f} x E"
 
 
 @pytest.mark.parametrize("k,case", [(3, "uniform"), (3, "clustered"), (16, "uniform"), (16, "mixed"), (128, "uniform"), (64, "offset1000"),
