@@ -41,6 +41,13 @@
 // 8 x 16 B core matrices for the 16-column steps, written by the prep kernels exactly as the UMMA
 // shared-memory descriptors expect them, so plain bulk copies suffice (no tensor maps).
 // SASS: UTCHMMA / LDTM / UBLKCP.
+//
+// F16 mode (round 2; THDR_MODE = TMODE_F16, plain layout, 10 <= k <= 128): F16 operands scaled by powers of two and F16
+// accumulators -- the epilogue reads two accumulators per register (tcgen05.ld ... pack::16b) and reduces them with
+// HMNMX2, which retires values at twice the rate of FMNMX3; its 58 registers leave room for three MMA-issuing threads
+// and three epilogue teams, with the query image in tensor memory and one accumulator buffer per (issuer, team).  The
+// scaling, the range guarantees and the error bound are in tensor_common.cuh ("F16 mode"); DESIGN.md 3.3 has the
+// measurements that led there.
 #include <algorithm>
 
 #include "tensor_common.cuh"
