@@ -201,6 +201,13 @@ int nns_b200_plan(int k, int m, int n, unsigned flags, int num_sms, int *plan);
  * (0 = BF16 operands with FP32 accumulators, 2 = F16 operands with F16 accumulators) } */
 int nns_b200_tensor_stats(unsigned *out4);
 
+/* host-side evaluation of the tcgen05 screen's error bound E(q) (pure function, no GPU needed; exported so that the
+ * tests' CPU emulation of the screen is checked against the shipped formula): a = |q - c|, rmax = max |r - c|,
+ * rmax_sampled = the sampled radius the F16 scale is derived from; mode 0 = the default BF16 operand layout of k,
+ * 2 = F16 operands and accumulators (10 <= k <= 128).  out4 = { E, reference scale s, query scale t (0 = the query
+ * cannot be screened), contraction columns }. */
+int nns_b200_tensor_bound(int k, int mode, float a, float rmax, float rmax_sampled, float *out4);
+
 /* number of kernels of this library launched by this process so far (bench.py's gpu_launches) */
 unsigned long long nns_b200_launch_count(void);
 

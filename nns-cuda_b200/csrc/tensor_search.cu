@@ -1786,3 +1786,26 @@ cudaError_t tensor_topk_search(int k, int m, int n, int K, const float* d_querie
 }
 
 }  // namespace nns
+
+// Host-side evaluation of the screen's error bound: a pure function of (k, mode, |q'|, max |r'|, sampled max |r'|), exported
+// so that the CPU emulation of the screen (tests/test_tensor_bound.py) is checked against the SHIPPED formula and
+// geometry, not against a copy of them.  out4 = { E(q), reference scale s, query scale t (0 = the query cannot be
+// screened), contraction columns }.  mode 0 = the default BF16 layout of k, 2 = F16.
+extern "C" int nns_b200_tensor_bound(int k, int mode, float a, float rmax, float rmax_sampled, float* out4)
+{
+    using namespace nns;
+    if (k < 1 || k > TENSOR_MAX_K || out4 == nullptr || (mode != 0 && mode != 2)) return 1;  // NNS_B200_ERR_INVALID
+    if (mode == 2 && !tensor_has_modes(k)) return 1;
+    const TensorGeom g = tensor_geom(k, mode == 2);
+    const int KP = g.KB * 64 + g.KS * 16;
+    float s = 1.0f, t = 1.0f, E;
+    if (mode == 2) {
+        s = tensor_f16_ref_scale(rmax_sampled);
+        t = tensor_f16_query_scale(s * a, s * rmax);
+        E = tensor_error_bound_f16(KP, k, a, rmax, s, t > 0.0f ? t : 1.0f, g.en != 0);
+    } else {
+        E = tensor_error_bound(g.split != 0, KP, a, rmax);
+    }
+    out4[0] = E; out4[1] = s; out4[2] = t; out4[3] = (float)KP;
+    return 0;
+}

@@ -61,6 +61,7 @@ lib.nns_b200_init.argtypes = [c_int]
 lib.nns_b200_shutdown.argtypes = []
 lib.nns_b200_cudaCall.argtypes = [c_int, c_int, c_int, _fp, _fp, POINTER(POINTER(c_int))]
 lib.nns_b200_cudaCall.restype = None
+lib.nns_b200_tensor_bound.argtypes = [c_int, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, POINTER(ctypes.c_float)]
 lib.nns_b200_search_host.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
 lib.nns_b200_search_host_dist.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
 lib.nns_b200_search_multi.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int]
@@ -259,6 +260,14 @@ def tensor_kp(k: int) -> int:
     if ndata <= 128:
         return 144
     return 64 * ((ndata + 3 + 63) // 64)
+
+
+def tensor_bound(k: int, mode: int, a: float, rmax: float, rmax_sampled: float) -> dict:
+    """The tcgen05 screen's error bound as the library evaluates it (host-side pure function; mode 0 = default BF16 layout,
+    2 = F16 operands and accumulators): {"E", "s" reference scale, "t" query scale (0: cannot be screened), "kp"}."""
+    out = (ctypes.c_float * 4)()
+    _check(lib.nns_b200_tensor_bound(int(k), int(mode), ctypes.c_float(a), ctypes.c_float(rmax), ctypes.c_float(rmax_sampled), out))
+    return {"E": float(out[0]), "s": float(out[1]), "t": float(out[2]), "kp": int(out[3])}
 
 
 def tensor_stats() -> dict:

@@ -193,3 +193,17 @@ def test_plan_overrides(nns):
     assert (p["q"], p["warps"], p["stages"]) == (8, 4, 3)
     with pytest.raises(nns.NnsError):
         nns.plan(3, 65536, 4194304, nns.flag_overrides(q=5) | nns.FLAG_FORCE_LOWK)
+
+
+def test_tensor_bound_is_a_pure_host_function(nns):
+    """nns_b200_tensor_bound needs no GPU: geometry, scales and E(q) of the tcgen05 screen for given norms"""
+    b = nns.tensor_bound(16, 0, 1.0, 1.2, 1.2)
+    assert b["kp"] == 64 and b["s"] == 1.0 and b["t"] == 1.0 and 0 < b["E"] < 1e-3      # split-precision BF16
+    f = nns.tensor_bound(16, 2, 1.0, 1.2, 1.2)
+    assert f["kp"] == 32 and f["s"] == 4.0 and f["t"] > 0 and b["E"] < f["E"] < 2e-2      # plain F16: a wider band, half the columns
+    assert nns.tensor_bound(128, 0, 3.0, 3.3, 3.3)["kp"] == 144
+    assert nns.tensor_bound(64, 2, 1e9, 1.0, 1.0)["t"] == 0.0                              # a query 1e9 radii out cannot be screened
+    assert nns.tensor_bound(64, 2, 1.0, 500.0, 1.0)["t"] == 0.0                            # nor can any, if the sample missed the radius 500x
+    for bad in ((0, 0), (510, 0), (9, 2), (129, 2), (16, 1)):
+        rc = nns.lib.nns_b200_tensor_bound(bad[0], bad[1], 1.0, 1.0, 1.0, (__import__("ctypes").c_float * 4)())
+        assert rc == nns.ERR_INVALID if hasattr(nns, "ERR_INVALID") else rc == 1

@@ -124,6 +124,7 @@ def screen_scores(k, s, r, plain=False):
     E = (c_round + F32(kp) * F32(2.04) * F32(4.7683716e-7)) * aa * rmax + F32(kp + 5) * u24 * r2 + F32(kp + 8) * u24 * (aa + rmax) * (aa + rmax)
     E = (E * F32(1.05)).astype(F32)
     qn64 = (qc.astype(np.float64) ** 2).sum(axis=1)
+    screen_scores.last = {"aa": aa, "rmax": rmax, "kp": kp}
     return acc, E, qn64
 
 
@@ -181,6 +182,7 @@ def screen_scores_f16(k, s, r, sample_step=5, epi_norm=None):
         + (u11 * F32(1.001) * rmax * rmax if en else F32(0.0)) + F32(kp + 5) * u24 * r2 + F32(kp + 8) * u24 * (aa + rmax) * (aa + rmax)
     E = (E * F32(1.05)).astype(F32)
     qn64 = (qc.astype(np.float64) ** 2).sum(axis=1)
+    screen_scores_f16.last = {"aa": aa, "rmax": rmax, "rmax_sampled": F32(np.sqrt(rn[::sample_step].max())), "kp": kp, "tq": tq, "sc": sc, "en": en}
     return S, E, qn64, usable
 
 
@@ -196,9 +198,22 @@ def v0_distances(s, r):
 CASES = ["uniform", "clustered", "offset1000", "scale1e-3", "mixed", "one_outlier"]
 
 
+def assert_library_bound(nns, k, mode, aa, rmax, rmax_sampled, E, kp, tq=None, sc=None):
+    """the E / scales / geometry this file computes == what the shipped library computes for the same inputs
+    (nns_b200_tensor_bound, a host-side pure function): the emulation tests the product's formula, not a copy of it"""
+    for i in range(0, len(aa), max(1, len(aa) // 8)):
+        b = nns.tensor_bound(k, mode, float(aa[i]), float(rmax), float(rmax_sampled))
+        assert b["kp"] == kp, (b, kp)
+        if mode == 2:
+            assert b["s"] == float(sc) and b["t"] == float(tq[i]), (b, float(sc), float(tq[i]))
+            if tq[i] == 0:
+                continue
+        assert abs(b["E"] - float(E[i])) <= 4e-6 * float(E[i]), (b, float(E[i]))  # same FP32 formula; association may differ by an ulp or two
+
+
 @pytest.mark.parametrize("k", [1, 3, 4, 9, 16, 42, 43, 64, 128, 129, 200, 320, 509, -10, -13, -16, -29, -30, -42, -61, -62, -64, -100, -125, -126, -128])
 @pytest.mark.parametrize("case", CASES)
-def test_screen_error_stays_inside_the_band(k, case):
+def test_screen_error_stays_inside_the_band(nns, k, case):
     plain, k = k < 0, abs(k)  # negative = the plain F16 mode (10 <= k <= 128)
     m, n = 48, 1536
     if case == "clustered" and k == 3:
@@ -224,8 +239,12 @@ def test_screen_error_stays_inside_the_band(k, case):
             return
         assert usable.all()
         assert np.isfinite(acc).all()  # no operand, no partial sum overflowed
+        L = screen_scores_f16.last
+        assert_library_bound(nns, k, 2, L["aa"], L["rmax"], L["rmax_sampled"], E, L["kp"], L["tq"], L["sc"])
     else:
         acc, E, qn64 = screen_scores(k, s, r, plain)
+        L = screen_scores.last
+        assert_library_bound(nns, k, 0, L["aa"], L["rmax"], L["rmax"], E, L["kp"])
     err = np.abs(acc.astype(np.float64) + qn64[:, None] - d)
     worst = (err / E[:, None].astype(np.float64)).max()
     assert worst <= 1.0, f"screen error reaches {worst:.3f} x E"
