@@ -458,6 +458,9 @@ def measure(name, args, env, steps, warmup, full=True):
         "config": workload_config(name, world, sharding_text(name, world, shard, strong_q), "flushed (256 MiB write) between timed steps"),
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         "plan": nns_b200.plan(k, m, r1 - r0, args.flags, nns_b200.device_sms()),
+        # the answer is decided by FP32 distances in V0's form; on the tcgen05 path a 16-bit screen (BF16 or F16 operands,
+        # see roofline.tensor_stats.mode) only selects which pairs get that exact evaluation
+        "dtype_note": "indices from exact FP32 distances; tensor-core screen in " + str((roofline.get("tensor_stats") or {}).get("mode", "n/a")),
     }
     if reduce_keys:
         rec["comm_ms"] = comm_total_ms / steps
