@@ -245,7 +245,8 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
     const float r2 = __uint_as_float(reinterpret_cast<const unsigned*>(hdr)[THDR_MAX]);
     const float a = sqrtf(qn), rmax = sqrtf(r2);
     const float s = f16 ? hdr[THDR_SCALE] : 1.0f;
-    const float tq = f16 ? tensor_f16_query_scale(s * a, s * rmax) : 1.0f;  // 0: not representable
+    float tq = f16 ? tensor_f16_query_scale(s * a, s * rmax) : 1.0f;        // 0: not representable
+    if (f16 && !(tq * s * s < inf_f())) tq = 0.0f;                            // u_q = t s^2 must be an FP32 number (extents below ~1e-17)
     const float xs = f16 ? -2.0f * tq * s : -2.0f;                            // power of two: exact
     const int chunks = g.KB * 8 + g.KS * 2;
     for (int ch = 0; ch < chunks; ++ch) {
@@ -267,7 +268,8 @@ tensor_query_image_kernel(const float* __restrict__ queries, const int m, const 
         // E(q) >= |S~ - S| + |d_V0 - D'| for every reference: tensor_error_bound / tensor_error_bound_f16 (tensor_common.cuh)
         const float E = f16 ? tensor_error_bound_f16(KP, k, a, rmax, s, tq > 0.0f ? tq : 1.0f, g.en != 0) : tensor_error_bound(g.split != 0, KP, a, rmax);
         const bool flagged = (reinterpret_cast<const unsigned*>(hdr)[THDR_FLAGS] & 1u) != 0;  // NaN / INF / huge / out-of-range references
-        const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f) && (tq > 0.0f);  // false for NaN too
+        // |r'|^2 below 1e-30 is computed from (nearly) denormal FP32 products: the 2^-24 relative terms of E do not hold
+        const bool usable = !flagged && (qn <= 1e30f) && (r2 <= 1e30f) && !(r2 > 0.0f && r2 < 1e-30f) && (tq > 0.0f);  // false for NaN too
         band[q] = usable ? 2.0f * E : inf_f();
         approx_min[q] = f2ord(inf_f());
         if (qscale) qscale[q] = f16 ? (tq > 0.0f ? tq * s * s : 1.0f) : 1.0f;

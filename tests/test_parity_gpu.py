@@ -711,6 +711,21 @@ def test_f16_mode_matches_v0(nns, oracle, torch_mod, k, m, n, kind):
     assert np.array_equal(g2, v2) and nns.tensor_stats()["mode"] == "f16"
 
 
+@pytest.mark.parametrize("k", [16, 64, 3])
+@pytest.mark.parametrize("scale", [1e-21, 1e-17, 1e-12])
+def test_tensor_screen_on_data_of_tiny_extent(nns, oracle, torch_mod, k, scale):
+    """Coordinates of 1e-21 .. 1e-12: FP32 norms and distances are (nearly) denormal, V0's own distances quantise to a
+    few values (many ties -> lowest index), the F16 scale would overflow FP32.  The screen must step aside (band = INF:
+    every unit is re-scored exactly, or the FP32 kernel takes over) and the answer must still be V0's, bit for bit."""
+    torch = torch_mod
+    m, n = 300, 20_000
+    s, r = make_case("uniform", k, m, n, 97)
+    s, r = (s.astype(np.float64) * scale).astype(np.float32), (r.astype(np.float64) * scale).astype(np.float32)
+    v, _ = oracle.v0_omp(k, m, n, s, r)
+    g = nns.DeviceIndex(dev(torch, r)).search(dev(torch, s), nns.FLAG_FORCE_TENSOR | nns.FLAG_V0_ROUNDING).cpu().numpy()
+    assert np.array_equal(g, v), (int((g != v).sum()), nns.tensor_stats())
+
+
 def test_f16_mode_reference_outside_the_sampled_radius_is_not_trusted(nns, oracle, torch_mod):
     """The F16 scale comes from a strided block sample.  A reference 1000 cloud radii out that the sample missed would
     overflow the 16-bit operands: the image kernel flags the section, every query then takes the exact path (all units
