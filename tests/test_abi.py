@@ -207,3 +207,14 @@ def test_tensor_bound_is_a_pure_host_function(nns):
     for bad in ((0, 0), (510, 0), (9, 2), (129, 2), (16, 1)):
         rc = nns.lib.nns_b200_tensor_bound(bad[0], bad[1], 1.0, 1.0, 1.0, (__import__("ctypes").c_float * 4)())
         assert rc == nns.ERR_INVALID if hasattr(nns, "ERR_INVALID") else rc == 1
+
+
+def test_screen_geometry_of_every_k_matches_the_python_mirror(nns):
+    """contraction columns of the operand images for every k, both modes: the library (nns_b200_tensor_bound) against the
+    mirrors the CPU emulation and bench.py use (tests/test_tensor_bound.geometry, nns_b200.tensor_kp)"""
+    from test_tensor_bound import geometry
+
+    for k in range(1, 510):
+        assert nns.tensor_bound(k, 0, 1.0, 1.0, 1.0)["kp"] == geometry(k)[0] == nns.tensor_kp(k), k
+        if 10 <= k <= 128:
+            assert nns.tensor_bound(k, 2, 1.0, 1.0, 1.0)["kp"] == geometry(k, True)[0], k
